@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Generate golden fixtures by EXECUTING THE REFERENCE'S OWN CODE in this container.
+
+Run once here (where /root/reference is mounted); the GPU box never reads /root/reference – it only reads the
+committed `.npz` files this script writes next to itself.
+
+What runs from the reference, unmodified:
+  * `gaussctrl/utils.py`  (CrossViewAttnProcessor, compute_attn) – imported from its file path with a stub
+    `diffusers.utils` module (USE_PEFT_BACKEND=True => `args=()`, i.e. lora scale unused; utils.py:54) and our
+    `oracle.crossview_attn.AttentionStub` standing in for diffusers' `Attention` module.
+  * `GaussCtrlPipeline.depth2disparity`, `.depth2disparity_torch` (gc_pipeline.py:248-266) and the ref-index
+    selection expressions (gc_pipeline.py:109-114) – extracted from the source with `ast` (the module itself
+    cannot be imported: nerfstudio/diffusers/lang_sam are absent) and executed as-is.
+"""
+import ast
+import importlib.util
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+REF = "/root/reference/gaussctrl"
+
+from oracle.crossview_attn import AttentionStub  # noqa: E402
+
+
+def load_reference_utils():
+    d = types.ModuleType("diffusers")
+    du = types.ModuleType("diffusers.utils")
+    du.USE_PEFT_BACKEND = True
+    d.utils = du
+    sys.modules.setdefault("diffusers", d)
+    sys.modules.setdefault("diffusers.utils", du)
+    spec = importlib.util.spec_from_file_location("ref_gaussctrl_utils", os.path.join(REF, "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def crossview_cases():
+    ref_utils = load_reference_utils()
+    out = {}
+    # (name, heads, dim_head, N, frames-per-half F, coeff, cross_dim or None, n_text)
+    cases = [
+        ("unet_R4c1", 2, 40, 32, 5, 0.6, None, 0),
+        ("unet_R4c3", 2, 40, 24, 7, 0.6, None, 0),
+        ("cnet_R4c3", 2, 40, 24, 7, 0.0, None, 0),
+        ("unet_d80", 2, 80, 16, 6, 0.6, None, 0),
+        ("text_cross", 2, 40, 24, 7, 0.6, 48, 11),
+    ]
+    for i, (name, heads, dh, n, f, coeff, cross, ntext) in enumerate(cases):
+        torch.manual_seed(1000 + i)
+        c = heads * dh
+        attn = AttentionStub(c, heads, dh, cross_attention_dim=cross)
+        b = 2 * f
+        hs = torch.randn(b, n, c)
+        ehs = torch.randn(b, ntext, cross) if cross is not None else None
+        proc = ref_utils.CrossViewAttnProcessor(self_attn_coeff=coeff, unet_chunk_size=2)
+        with torch.no_grad():
+            y = proc(attn, hs, encoder_hidden_states=ehs)
+        out[f"{name}.meta"] = np.array([heads, dh, n, f, cross or 0, ntext], dtype=np.int64)
+        out[f"{name}.coeff"] = np.array([coeff], dtype=np.float64)
+        out[f"{name}.hidden"] = hs.numpy()
+        if ehs is not None:
+            out[f"{name}.ehs"] = ehs.numpy()
+        for k_, v_ in attn.state_dict().items():
+            out[f"{name}.w.{k_}"] = v_.numpy()
+        out[f"{name}.out"] = y.numpy()
+    np.savez_compressed(os.path.join(HERE, "crossview_reference.npz"), **out)
+    print("crossview_reference.npz:", len(cases), "cases")
+
+
+def extract_methods(path, class_name, names):
+    src = open(path).read()
+    tree = ast.parse(src)
+    found = {}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name in names:
+                    item.decorator_list = []
+                    found[item.name] = item
+    ns = {"np": np, "torch": torch}
+    modtree = ast.Module(body=[found[n] for n in names], type_ignores=[])
+    exec(compile(modtree, path, "exec"), ns)
+    return {n: ns[n] for n in names}, src
+
+
+def glue_cases():
+    fns, src = extract_methods(os.path.join(REF, "gc_pipeline.py"), "GaussCtrlPipeline",
+                               ["depth2disparity", "depth2disparity_torch"])
+    rng = np.random.default_rng(7)
+    depth = rng.uniform(0.3, 12.0, size=(1, 16, 16)).astype(np.float32)
+    depth[0, 0, :4] = 1000.0  # the "alpha == 0" fill value of gc_model.py:204
+    disp_np = fns["depth2disparity"](None, depth)
+    disp_t = fns["depth2disparity_torch"](None, torch.from_numpy(depth).to(torch.float16))
+    out = {"depth": depth, "disparity_np": disp_np, "disparity_torch_f16": disp_t.float().numpy()}
+
+    # ref-index selection: execute the reference's own expressions (gc_pipeline.py:109-114), located textually
+    # so a change in the reference would break this script instead of silently diverging.
+    anchors_line = "anchors = [(view_num * i) // self.config.ref_view_num for i in range(self.config.ref_view_num)] + [view_num]"
+    pick_line = "self.ref_indices = [random.randint(anchor, anchors[idx+1]) for idx, anchor in enumerate(anchors[:-1])]"
+    assert anchors_line in src and pick_line in src and "random.seed(13789)" in src
+    rows = []
+    for view_num, r in [(40, 4), (40, 8), (80, 4), (128, 8), (1, 1), (96, 4), (185, 4)]:
+        self = types.SimpleNamespace(config=types.SimpleNamespace(ref_view_num=r))
+        ns = {"self": self, "view_num": view_num, "random": random}
+        exec(anchors_line, ns)
+        random.seed(13789)
+        exec(pick_line, ns)
+        rows.append((view_num, r, list(self.ref_indices)))
+        out[f"ref_indices.V{view_num}.R{r}"] = np.array(self.ref_indices, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "glue_reference.npz"), **out)
+    print("glue_reference.npz:", rows)
+
+
+if __name__ == "__main__":
+    assert os.path.isdir(REF), "run this where /root/reference is mounted"
+    crossview_cases()
+    glue_cases()
