@@ -1,0 +1,365 @@
+// Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (kind::f16) -> TMEM accumulator
+//   -> tcgen05.ld epilogue (bias / per-image vector / residual / SiLU / GEGLU) -> fp16 store.
+//
+// y[M, Cout] = act( im2col(x)[M, taps*Cin] * w[Cout, taps*Cin]^T + bias + rowvec[b] ) + residual
+//
+// A operand: the NHWC activation tensor is described to TMA as a 4-D tensor (C, W, H, B).  One M tile = 128
+// consecutive output pixels = a (bw x bh x bb) pixel box; filter tap (kh,kw) is the SAME box shifted by
+// (kw-1, kh-1) – TMA's out-of-bounds zero fill implements the padding, so no im2col buffer ever exists.
+// B operand: w is [Cout, taps*Cin] (K contiguous) -> 2-D TMA box (64 x BN).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (each owns the 32 TMEM lanes (warp_id % 4) * 32 ...).
+#include "../../include/gaussctrl_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 halves = 128 B = one swizzle-128B atom row
+constexpr int MAX_STAGES = 8;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmTcParams {
+    int M, N;          // GEMM sizes (N = Cout)
+    int nkb;           // total K blocks
+    int kb_per_tap;    // Cin / 64 (conv) or nkb (linear)
+    int mode;          // 0 = linear (2-D A map), 1 = conv3x3 (4-D A map)
+    int H, W, HW;
+    int bw, bh, bb;    // pixel box of one M tile
+    int BN, stages;
+    uint32_t tmem_cols, idesc;
+    const __half* bias;
+    const __half* rowvec;
+    int rowvec_ld;
+    const __half* residual;
+    __half* y;
+    int ldy;
+    int act;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) { return act == GCB_ACT_SILU ? silu_f(v) : v; }
+
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_stage_bytes = (uint32_t)p.BN * BK * 2;
+    const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            int b0 = 0, h0 = 0, w0 = 0;
+            if (p.mode == 1) {
+                if (p.HW >= BM) {
+                    const int tiles_per_img = p.HW / BM;
+                    b0 = m_tile / tiles_per_img;
+                    const int r = m_tile % tiles_per_img;
+                    if (p.W >= BM) {
+                        const int segs = p.W / BM;
+                        h0 = r / segs;
+                        w0 = (r % segs) * BM;
+                    } else {
+                        h0 = r * p.bh;
+                    }
+                } else {
+                    b0 = m_tile * p.bb;
+                }
+            }
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                mbar_expect_tx(fb, stage_bytes);
+                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                const uint32_t sb = sa + A_STAGE_BYTES;
+                if (p.mode == 0) {
+                    tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * BM);
+                } else {
+                    const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    tma_load_4d(sa, &tmA, fb, cb * BK, w0 + kw - 1, h0 + kh - 1, b0);
+                }
+                tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * p.BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                tc_fence_after();
+                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                const uint32_t sb = sa + A_STAGE_BYTES;
+                const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
+                const uint64_t bdesc = make_smem_desc(sb, 16, 1024, 2);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advance 16 halves = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+                    tc_mma_ss(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc,
+                              (uint32_t)((kb | k) != 0));
+                }
+                tc_commit(smem_u32(&empty_bar[s]));
+            }
+            tc_commit(smem_u32(&tmem_full_bar));
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const long long m = (long long)m_tile * BM + row;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool row_ok = m < p.M;
+        const int img = (p.rowvec != nullptr && row_ok) ? (int)(m / p.HW) : 0;
+        if (p.act != GCB_ACT_GEGLU) {
+            const int nchunks = p.BN / 32;
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+                tc_wait_ld();
+                const int n0 = n_tile * p.BN + c * 32;
+                if (!row_ok || n0 >= p.N) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                const int nvalid = min(32, p.N - n0);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nvalid) v[j] += __half2float(p.bias[n0 + j]);
+                }
+                if (p.rowvec) {
+                    const __half* rv = p.rowvec + (long long)img * p.rowvec_ld + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nvalid) v[j] += __half2float(rv[j]);
+                }
+                if (p.act == GCB_ACT_SILU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                }
+                __half* yp = p.y + m * p.ldy + n0;
+                if (nvalid == 32) {
+                    if (p.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldy + n0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint4 rr = rp[g];
+                            const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 f = unpack_half2(w[t]);
+                                v[g * 8 + t * 2] += f.x;
+                                v[g * 8 + t * 2 + 1] += f.y;
+                            }
+                        }
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(yp);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 o;
+                        o.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]);
+                        o.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
+                        o.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]);
+                        o.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
+                        op[g] = o;
+                    }
+                } else {
+                    for (int j = 0; j < nvalid; ++j) {
+                        float o = v[j];
+                        if (p.residual) o += __half2float(p.residual[m * p.ldy + n0 + j]);
+                        yp[j] = __float2half_rn(o);
+                    }
+                }
+            }
+        } else {
+            // GEGLU: tile columns [0, BN/2) = value, [BN/2, BN) = gate; output width N/2
+            const int half_bn = p.BN / 2;
+            const int n_out = p.N / 2;
+            for (int c = 0; c < half_bn / 32; ++c) {
+                uint32_t rv[32], rg[32];
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), rv);
+                tmem_ld_32x32b_x32(taddr + (uint32_t)(half_bn + c * 32), rg);
+                tc_wait_ld();
+                const int t0 = n_tile * p.BN;                 // packed-row offset of this tile
+                const int o0 = n_tile * half_bn + c * 32;     // output column
+                if (!row_ok || o0 >= n_out) continue;
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float val = __uint_as_float(rv[j]);
+                    float gate = __uint_as_float(rg[j]);
+                    if (p.bias) {
+                        val += __half2float(p.bias[t0 + c * 32 + j]);
+                        gate += __half2float(p.bias[t0 + half_bn + c * 32 + j]);
+                    }
+                    o[j] = val * gelu_erf_f(gate);
+                }
+                uint4* op = reinterpret_cast<uint4*>(p.y + m * p.ldy + o0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u;
+                    u.x = pack_half2(o[g * 8 + 0], o[g * 8 + 1]);
+                    u.y = pack_half2(o[g * 8 + 2], o[g * 8 + 3]);
+                    u.z = pack_half2(o[g * 8 + 4], o[g * 8 + 5]);
+                    u.w = pack_half2(o[g * 8 + 6], o[g * 8 + 7]);
+                    op[g] = u;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+int choose_bn(int M, int N, int act) {
+    if (act == GCB_ACT_GEGLU) return gcb_geglu_tile_n(N);
+    const int cands[4] = {256, 160, 128, 64};
+    int best = 64;
+    long long best_pad = -1;
+    for (int i = 0; i < 4; ++i) {
+        const int bn = cands[i];
+        const long long pad = (long long)gcb_cdiv(N, bn) * bn;
+        if (best_pad < 0 || pad < best_pad) {
+            best_pad = pad;
+            best = bn;
+        }
+    }
+    // small problems: prefer more CTAs over bigger tiles
+    const long long mt = gcb_cdiv(M, BM);
+    while (best > 64 && mt * gcb_cdiv(N, best) < gcb_sm_count() && (N % (best / 2) == 0 || best == 160)) {
+        best = best == 160 ? 64 : best / 2;
+    }
+    return best;
+}
+
+}  // namespace
+
+extern "C" int gcb_geglu_tile_n(int Cout) { return ((Cout / 2) % 128 == 0) ? 256 : 128; }
+
+// perm[r_packed] = source row in the diffusers [value(4C) ; gate(4C)] projection
+extern "C" int gcb_geglu_pack_rows(int Cout, int32_t* h_perm) {
+    GCB_CHECK_ARG(Cout > 0 && Cout % 128 == 0, "GEGLU Cout=%d must be a multiple of 128", Cout);
+    const int bn = gcb_geglu_tile_n(Cout), half = bn / 2, n_out = Cout / 2;
+    for (int t = 0; t < Cout / bn; ++t)
+        for (int j = 0; j < half; ++j) {
+            h_perm[t * bn + j] = t * half + j;
+            h_perm[t * bn + half + j] = n_out + t * half + j;
+        }
+    return GCB_OK;
+}
+
+int gcb_gemm_tc_supported(int B, int H, int W, int Cin, int Cout, int ksize, int act) {
+    if (Cout % 8 != 0 || Cin % 8 != 0) return 0;
+    if (act == GCB_ACT_GEGLU && Cout % 128 != 0) return 0;
+    if (ksize == 1) return 1;
+    if (ksize != 3 || Cin % BK != 0) return 0;
+    // pixel box: W must tile 128 (or be tiled by it), H must be a multiple of the box height
+    if (W >= BM) return (W % BM == 0);
+    if (BM % W != 0) return 0;
+    const int bh = (H * W >= BM) ? BM / W : H;
+    if (H % bh != 0) return 0;
+    if (H * W < BM && BM % (H * W) != 0) return 0;
+    return 1;
+}
+
+int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
+                       const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
+                       cudaStream_t stream) {
+    GemmTcParams p;
+    memset(&p, 0, sizeof(p));
+    const long long M = (long long)B * H * W;
+    const int taps = ksize * ksize;
+    const int Ktot = taps * Cin;
+    p.M = (int)M;
+    p.N = Cout;
+    p.mode = (ksize == 3) ? 1 : 0;
+    p.H = H;
+    p.W = W;
+    p.HW = H * W;
+    p.BN = choose_bn((int)M, Cout, act);
+    p.kb_per_tap = (ksize == 3) ? Cin / BK : gcb_cdiv(Cin, BK);
+    p.nkb = taps * p.kb_per_tap;
+    const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
+    int budget = 112 * 1024;
+    if (const char* e = getenv("GCB_GEMM_SMEM_KB")) budget = atoi(e) * 1024;
+    p.stages = budget / stage_bytes;
+    if (p.stages < 2) p.stages = 2;
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    if (p.stages > p.nkb) p.stages = p.nkb < 2 ? 2 : p.nkb;
+    p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+    p.idesc = make_idesc_f16(BM, p.BN, 0, 0);
+    p.bias = (const __half*)bias;
+    p.rowvec = (const __half*)rowvec;
+    p.rowvec_ld = rowvec_ld;
+    p.residual = (const __half*)residual;
+    p.y = (__half*)y;
+    p.ldy = (act == GCB_ACT_GEGLU) ? Cout / 2 : Cout;
+    p.act = act;
+
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (p.mode == 0) {
+        const uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)M};
+        const uint64_t strides[1] = {(uint64_t)Cin * 2};
+        const uint32_t box[2] = {BK, BM};
+        rc = gcb_encode_tma(&tmA, x, 2, dims, strides, box, 1);
+    } else {
+        p.bw = W >= BM ? BM : W;
+        p.bh = (H * W >= BM) ? (BM / p.bw) : H;
+        p.bb = (H * W >= BM) ? 1 : BM / (H * W);
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        const uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bb};
+        rc = gcb_encode_tma(&tmA, x, 4, dims, strides, box, 1);
+    }
+    if (rc != GCB_OK) return rc;
+    {
+        const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)Cout};
+        const uint64_t strides[1] = {(uint64_t)Ktot * 2};
+        const uint32_t box[2] = {BK, (uint32_t)p.BN};
+        rc = gcb_encode_tma(&tmB, w, 2, dims, strides, box, 1);
+        if (rc != GCB_OK) return rc;
+    }
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    static size_t configured_smem = 0;
+    if (smem > configured_smem) {
+        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured_smem = 227 * 1024;
+    }
+    dim3 grid(gcb_cdiv(Cout, p.BN), gcb_cdiv(M, BM));
+    gemm_tc_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, p);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}

@@ -1,0 +1,202 @@
+/* gaussctrl_b200 – C ABI of the B200-native GaussCtrl hot path (libgaussctrl_b200.so).
+ *
+ * The reference (ActiveVisionLab/gaussctrl) has no FFI of its own: its hot path calls two third-party Python
+ * operator sets (gsplat 0.1.3, diffusers 0.26.0).  Each entry point below replaces the native work behind one
+ * of those Python call sites; the citation says which (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_` (host);
+ *   - the caller owns every buffer, including workspaces sized by the *_workspace_bytes queries; nothing is
+ *     allocated, freed or synchronised inside (exceptions are documented per function);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it (CUDA-graph capturable);
+ *   - return value: 0 = ok, negative = error (GCB_ERR_*); `gcb_last_error()` returns a thread-local message;
+ *   - fp16 tensors are IEEE binary16 ("half"); activations are channels-last: images [B,H,W,C], tokens [B,N,C].
+ */
+#ifndef GAUSSCTRL_B200_H
+#define GAUSSCTRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCB_VERSION 100
+
+#define GCB_ERR_INVALID (-1)     /* bad argument / unsupported shape */
+#define GCB_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
+#define GCB_ERR_UNSUPPORTED (-3) /* valid request, kernel variant not built */
+#define GCB_ERR_WORKSPACE (-4)   /* workspace too small */
+
+int gcb_version(void);
+const char* gcb_last_error(void);
+int gcb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ======================================================================================================
+ * A. Diffusion side – replaces the cuDNN/cuBLAS/eager kernels diffusers launches from
+ *    `self.pipe(...)` (gaussctrl/gc_pipeline.py:142-145 and :209-219) and `self.pipe.vae.encode`
+ *    (gc_pipeline.py:244).
+ * ====================================================================================================== */
+
+/* Epilogue activation of gcb_conv2d_nhwc_fwd */
+#define GCB_ACT_NONE 0
+#define GCB_ACT_SILU 1
+#define GCB_ACT_GEGLU 2 /* weights packed [value-half | gate-half] per N tile: see gcb_geglu_pack_rows */
+
+/* GEMM implementation selector (debug / bisecting; the product default is GCB_GEMM_TCGEN05) */
+#define GCB_GEMM_TCGEN05 0 /* TMA + tcgen05.mma + TMEM accumulators */
+#define GCB_GEMM_MMA_SYNC 1 /* legacy mma.sync path kept for bring-up comparison */
+
+/* Implicit-GEMM convolution / linear layer, fp16 in/out, fp32 accumulate.
+ *   x        [B,H,W,Cin]                 (Linear: B=1,H=1,W=M rows)
+ *   w        [Cout, ksize*ksize*Cin]     tap-major, channel-minor ("OHWI")
+ *   bias     [Cout] or NULL
+ *   rowvec   [B, rowvec_ld] or NULL      per-image vector added to every pixel (ResnetBlock2D time_emb_proj)
+ *   residual [B*H*W, Cout] or NULL       added after bias (+ rowvec)
+ *   y        [B*H*W, Cout]               (GCB_ACT_GEGLU: [B*H*W, Cout/2])
+ *   ksize    1 or 3 (stride 1, padding ksize/2).  Stride-2 convs go through gcb_im2col_nhwc + ksize=1.
+ * Replaces: torch.nn.Conv2d / Linear inside UNet2DConditionModel, ControlNetModel, AutoencoderKL. */
+int gcb_conv2d_nhwc_fwd(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
+                        const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
+                        int impl, void* stream);
+
+/* Direct convolution for tiny channel counts (conv_in 4->320, conv_out 320->4, ControlNet cond embedding,
+ * VAE conv_in/conv_out).  Any Cin/Cout, ksize 1|3, stride 1|2, pad_lo/pad_hi (VAE downsample pads (0,1)). */
+int gcb_conv2d_direct_nhwc_fwd(const void* x, const void* w, const void* bias, const void* residual, void* y, int B,
+                               int H, int W, int Cin, int Cout, int ksize, int stride, int pad_lo, int pad_hi, int act,
+                               void* stream);
+
+/* im2col for 3x3 stride-2 convolutions (Downsample2D): x [B,H,W,C] -> col [B*Ho*Wo, 9*C]. */
+int gcb_im2col3x3_s2_nhwc(const void* x, void* col, int B, int H, int W, int C, int pad_lo, int pad_hi, void* stream);
+
+/* Row permutation that turns a diffusers GEGLU projection [8C, C] into the tile-interleaved layout
+ * GCB_ACT_GEGLU expects.  h_perm (host, int32[Cout]) receives source-row indices; tile_n is the N tile used. */
+int gcb_geglu_tile_n(int Cout);
+int gcb_geglu_pack_rows(int Cout, int32_t* h_perm);
+
+/* GroupNorm (+ optional SiLU) over channels-last input, optionally over the channel-concatenation of two
+ * tensors (UNet skip connections): y[B,HW,C1+C2] = act(GN(cat(x1, x2))).  fp32 statistics.
+ * Replaces: torch.nn.GroupNorm + F.silu in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out. */
+int gcb_groupnorm_nhwc_fwd(const void* x1, const void* x2, const void* gamma, const void* beta, void* y, int B, int HW,
+                           int C1, int C2, int groups, float eps, int silu, void* stream);
+
+/* LayerNorm over the last dim: y[M,C]. Replaces torch.nn.LayerNorm in BasicTransformerBlock. */
+int gcb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int M, int C, float eps,
+                      void* stream);
+
+/* Multi-source attention = the fused form of CrossViewAttnProcessor (gaussctrl/utils.py:44-133, compute_attn :25-37):
+ *     out[b] = sum_s weight[s] * softmax(q[b] K_s^T * scale) V_s          (independent softmax per source, per head)
+ * q [B,Nq,heads*d]; K/V sources live in two buffers: (k,v) [Bkv,Nk,heads*d] and (k2,v2) [Bkv2,Nk,heads*d].
+ * src_index (device int32 [B*n_src]): for query row b and source s, the batch row to read; values >= 0 index (k,v),
+ * values < 0 index (k2,v2) at row -(value+1).  h_src_weight: host float[n_src]; zero-weight sources are skipped.
+ * The reference's 5 passes are n_src=5, weights {c, (1-c)/4 x4}, src rows {b, ref0..ref3 of b's CFG half}
+ * (utils.py:88-117); text cross-attention and the vanilla AttnProcessor are n_src=1.
+ * ld_* are row strides in elements (>= heads*d) so q/k/v may be slices of a fused QKV projection. */
+int gcb_attn_multi_fwd(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2,
+                       const void* v2, int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d,
+                       int n_src, const int32_t* src_index, const float* h_src_weight, float scale, void* stream);
+
+/* Row softmax with scale, fp16 in/out, fp32 math (VAE mid-block attention, 1 head of dim 512). */
+int gcb_softmax_rows_fwd(const void* x, void* y, int rows, int cols, float scale, void* stream);
+
+/* Elementwise / data-movement helpers of the denoising loop */
+int gcb_silu_fwd(const void* x, void* y, long long n, void* stream);
+int gcb_add_fwd(const void* a, const void* b, void* y, long long n, float alpha, float beta, void* stream);
+int gcb_geglu_fwd(const void* x, void* y, int M, int C, void* stream); /* x [M,2C] -> y [M,C] = x[:, :C]*gelu(x[:, C:]) */
+int gcb_upsample_nearest2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
+int gcb_timestep_embedding(const float* h_timesteps, int B, int dim, void* y /* fp16 [B,dim] */, void* stream);
+int gcb_nchw_to_nhwc_f16(const void* x, void* y, int B, int C, int H, int W, void* stream);
+int gcb_nhwc_to_nchw_f16(const void* x, void* y, int B, int C, int H, int W, void* stream);
+int gcb_transpose_f16(const void* x, void* y, int rows, int cols, void* stream);
+
+/* Classifier-free-guidance combine + DDIM step (eta = 0), replaces
+ * `noise_pred_uncond + g*(noise_pred_text - noise_pred_uncond)` and `DDIMScheduler.step` inside pipe() (:209-219);
+ * with eps_cond == NULL it is the plain (inverse) DDIM update used by DDIMInverseScheduler (:141-145).
+ *   x' = sqrt(a_prev) * (x - sqrt(1-a_t) * eps) / sqrt(a_t) + sqrt(1-a_prev) * eps       (fp32 math, fp16 storage) */
+int gcb_cfg_ddim_step(const void* eps_uncond, const void* eps_cond, const void* x, void* x_out, long long n,
+                      float guidance, float alpha_t, float alpha_prev, void* stream);
+
+/* (x/2+0.5).clamp(0,1) on the decoded image + optional mask composite edited*m + unedited*(1-m)
+ * (gc_pipeline.py:223-234); img [B,H,W,3] fp16 NHWC -> out [B,H,W,3] fp32. mask [B,H,W] fp32 or NULL. */
+int gcb_postprocess_composite(const void* img, const float* mask, const void* unedited_f16, float* out, int B, int H,
+                              int W, void* stream);
+
+/* disparity = (1/(depth+1e-5)) / max(...) replicated to 3 channels (gc_pipeline.py:248-266); depth fp32 [B,H,W]
+ * -> fp16 [B,H,W,3]; the max is per image.  workspace: B floats. */
+int gcb_depth_to_disparity(const float* depth, void* disp_f16, float* workspace, int B, int HW, int round_f16_first,
+                           void* stream);
+
+/* ======================================================================================================
+ * B. Rasterisation side – replaces gsplat's CUDA extension behind
+ *    project_gaussians (gc_model.py:140-154), spherical_harmonics (:166), rasterize_gaussians (:174-186,:191-202).
+ * ====================================================================================================== */
+
+/* gsplat.project_gaussians forward. h_viewmat: host float[16] row-major world->camera (only rows 0..2 used);
+ * h_projmat: host float[16] full projection.  Outputs: xys [N,2], depths [N], radii [N] i32, conics [N,3],
+ * num_tiles_hit [N] i32, cov3d [N,6] (cov3d may be NULL).  fp32, bit-exact vs the oracle (no FMA contraction). */
+int gcb_project_gaussians_fwd(const float* means3d, const float* scales, float glob_scale, const float* quats,
+                              const float* h_viewmat, const float* h_projmat, float fx, float fy, float cx, float cy,
+                              int img_h, int img_w, int tile_bx, int tile_by, float clip_thresh, int N, float* xys,
+                              float* depths, int32_t* radii, float* conics, int32_t* num_tiles_hit, float* cov3d,
+                              void* stream);
+
+/* gsplat.spherical_harmonics forward: viewdirs [N,3] (unit), coeffs [N,K,3], colors [N,3]. */
+int gcb_sh_fwd(int degree, int K, const float* viewdirs, const float* coeffs, float* colors, int N, void* stream);
+/* backward: v_coeffs [N,K,3] (written, zero beyond the active degree) */
+int gcb_sh_bwd(int degree, int K, const float* viewdirs, const float* v_colors, float* v_coeffs, int N, void* stream);
+
+/* Fused B200 path of GaussCtrlModel.get_outputs (gc_model.py:138-167): exp(scales), quat normalisation,
+ * projection, view direction, SH colour (+0.5, clamp >= 0) and sigmoid(opacity) in ONE pass over the
+ * 236 B/Gaussian parameter record.  Outputs as gcb_project_gaussians_fwd plus rgbs [N,3], opac [N]. */
+int gcb_project_sh_fused_fwd(const float* means3d, const float* log_scales, const float* quats,
+                             const float* features_dc, const float* features_rest, const float* opacity_logits,
+                             const float* h_viewmat, const float* h_projmat, const float* h_cam_origin, float fx,
+                             float fy, float cx, float cy, int img_h, int img_w, int tile_bx, int tile_by,
+                             int sh_degree, int N, float* xys, float* depths, int32_t* radii, float* conics,
+                             int32_t* num_tiles_hit, float* rgbs, float* opac, void* stream);
+
+/* Inclusive prefix sum of num_tiles_hit -> cum_tiles_hit (int32 [N]); workspace via gcb_scan_workspace_bytes. */
+size_t gcb_scan_workspace_bytes(int N);
+int gcb_cumsum_i32(const int32_t* in, int32_t* out, int N, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Tile binning: map_gaussian_to_intersects + stable radix sort by (tile_id << 32 | depth bits) + tile bin edges.
+ * M = cum_tiles_hit[N-1] (the caller reads it back, as gsplat does). Outputs: isect_keys [M] i64 (sorted),
+ * gaussian_ids [M] i32 (sorted), tile_bins [tile_bx*tile_by, 2] i32. */
+size_t gcb_bin_sort_workspace_bytes(int N, long long M);
+int gcb_bin_and_sort(const float* xys, const float* depths, const int32_t* radii, const int32_t* cum_tiles_hit, int N,
+                     long long M, int tile_bx, int tile_by, int64_t* isect_keys, int32_t* gaussian_ids,
+                     int32_t* tile_bins, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Per-tile front-to-back alpha compositing (gsplat rasterize_forward).  colors [N,C] with C in {1,3,4};
+ * background host float[C].  Outputs: out_img [H,W,C], final_T [H,W], final_idx [H,W] i32.
+ * C=4 with colors = (r,g,b,depth) is the fused rgb+depth pass that replaces the reference's TWO rasterize calls
+ * (gc_model.py:174-202). */
+int gcb_rasterize_fwd(const float* xys, const float* conics, const float* colors, const float* opacities,
+                      const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
+                      const float* h_background, float* out_img, float* final_T, int32_t* final_idx, void* stream);
+
+/* gsplat rasterize_backward: v_out [H,W,C] (and optional v_out_alpha [H,W]) -> v_xy [N,2], v_conic [N,3],
+ * v_colors [N,C], v_opacity [N] (all must be zero-initialised by the caller; accumulated with atomics). */
+int gcb_rasterize_bwd(const float* xys, const float* conics, const float* colors, const float* opacities,
+                      const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
+                      const float* h_background, const float* final_T, const int32_t* final_idx, const float* v_out,
+                      const float* v_out_alpha, float* v_xy, float* v_conic, float* v_colors, float* v_opacity,
+                      void* stream);
+
+/* gsplat project_gaussians backward: (v_xy, v_depth, v_conic) -> v_means3d [N,3], v_scales [N,3], v_quats [N,4]. */
+int gcb_project_gaussians_bwd(const float* means3d, const float* scales, float glob_scale, const float* quats,
+                              const float* h_viewmat, const float* h_projmat, float fx, float fy, float cx, float cy,
+                              int img_h, int img_w, const int32_t* radii, const float* conics, const float* v_xy,
+                              const float* v_depth, const float* v_conic, int N, float* v_means3d, float* v_scales,
+                              float* v_quats, void* stream);
+
+/* get_outputs epilogue (gc_model.py:188,203-204): rgb = min(rgb,1); depth = depth/alpha where alpha>0 else 1000.
+ * in: img4 [H,W,4] (r,g,b,depth-accum), final_T [H,W]; out: rgb [H,W,3], depth [H,W,1], alpha [H,W,1]. */
+int gcb_raster_finalize(const float* img4, const float* final_T, float* rgb, float* depth, float* alpha, int HW,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAUSSCTRL_B200_H */
