@@ -312,7 +312,7 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
     p.kb_per_tap = (ksize == 3) ? Cin / BK : gcb_cdiv(Cin, BK);
     p.nkb = taps * p.kb_per_tap;
     const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
-    int budget = 112 * 1024;
+    int budget = 200 * 1024;
     if (const char* e = getenv("GCB_GEMM_SMEM_KB")) budget = atoi(e) * 1024;
     p.stages = budget / stage_bytes;
     if (p.stages < 2) p.stages = 2;

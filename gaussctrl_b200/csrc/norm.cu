@@ -1,0 +1,227 @@
+// GroupNorm (+SiLU, + channel-concat of two inputs) and LayerNorm over channels-last fp16 tensors, fp32 statistics.
+// Replaces torch.nn.GroupNorm/F.silu in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out and
+// torch.nn.LayerNorm in BasicTransformerBlock (diffusers 0.26.0, invoked from gc_pipeline.py:142-145, 209-219).
+// Both are HBM-bound: GroupNorm = 2 reads + 1 write of the tensor (stats pass is L2-resident for the second read
+// at UNet sizes), LayerNorm = 1 read + 1 write.  Deterministic: partial sums are reduced in a fixed order.
+#include "../../include/gaussctrl_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int GN_MAX_GROUPS = 32;
+constexpr int GN_MAX_CHUNKS = 64;
+
+__device__ __forceinline__ const __half* gn_src(const __half* x1, const __half* x2, int C1, int C2, long long pix,
+                                                int c) {
+    return c < C1 ? x1 + pix * C1 + c : x2 + pix * C2 + (c - C1);
+}
+
+// partial[b][chunk][g][2] = (sum, sumsq) over the chunk's pixels
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2,
+                                                       float* __restrict__ partial, int HW, int C1, int C2, int groups,
+                                                       int pix_per_chunk) {
+    __shared__ float s_sum[GN_MAX_GROUPS], s_sq[GN_MAX_GROUPS];
+    const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const int C = C1 + C2, cols = C / 2, cpg = C / groups;
+    if (tid < groups) {
+        s_sum[tid] = 0.f;
+        s_sq[tid] = 0.f;
+    }
+    __syncthreads();
+    const int p0 = chunk * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
+    const int rgroups = cols >= 256 ? 1 : 256 / cols;
+    const int rg = cols >= 256 ? 0 : tid / cols;
+    if (rg < rgroups) {
+        for (int col = cols >= 256 ? tid : tid % cols; col < cols; col += 256) {
+            const int c = col * 2;
+            float sum = 0.f, sq = 0.f;
+            for (int p = p0 + rg; p < p1; p += rgroups) {
+                const long long pix = (long long)b * HW + p;
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(gn_src(x1, x2, C1, C2, pix, c)));
+                sum += f.x + f.y;
+                sq += f.x * f.x + f.y * f.y;
+            }
+            atomicAdd(&s_sum[c / cpg], sum);
+            atomicAdd(&s_sq[c / cpg], sq);
+            if (cols < 256) break;
+        }
+    }
+    __syncthreads();
+    if (tid < groups) {
+        float* o = partial + (((long long)b * gridDim.x + chunk) * groups + tid) * 2;
+        o[0] = s_sum[tid];
+        o[1] = s_sq[tid];
+    }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2,
+                                                       const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                                       const float* __restrict__ partial, __half* __restrict__ y, int HW,
+                                                       int C1, int C2, int groups, int nchunks, int pix_per_cta,
+                                                       float eps, int silu) {
+    extern __shared__ float s_ab[];  // a[C], b[C]
+    __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int C = C1 + C2, cpg = C / groups;
+    if (tid < groups) {
+        float sum = 0.f, sq = 0.f;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const float* pp = partial + (((long long)b * nchunks + ch) * groups + tid) * 2;
+            sum += pp[0];
+            sq += pp[1];
+        }
+        const float n = (float)HW * (float)cpg;
+        const float mean = sum / n;
+        const float var = fmaxf(sq / n - mean * mean, 0.f);
+        s_mean[tid] = mean;
+        s_rstd[tid] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    float* sa = s_ab;
+    float* sb = s_ab + C;
+    for (int c = tid; c < C; c += 256) {
+        const int g = c / cpg;
+        const float a = s_rstd[g] * __half2float(gamma[c]);
+        sa[c] = a;
+        sb[c] = __half2float(beta[c]) - s_mean[g] * a;
+    }
+    __syncthreads();
+    const int cv = C / 8;
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    const long long total = (long long)(p1 - p0) * cv;
+    for (long long i = tid; i < total; i += 256) {
+        const int v = (int)(i % cv);
+        const long long pix = (long long)b * HW + p0 + i / cv;
+        const int c = v * 8;
+        const uint4 raw = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_half2(w[t]);
+            float r0 = f.x * sa[c + 2 * t] + sb[c + 2 * t];
+            float r1 = f.y * sa[c + 2 * t + 1] + sb[c + 2 * t + 1];
+            if (silu) {
+                r0 = silu_f(r0);
+                r1 = silu_f(r1);
+            }
+            o[t] = pack_half2(r0, r1);
+        }
+        *reinterpret_cast<uint4*>(y + pix * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// one warp per row, row held in registers (C <= 8*32*MAXV)
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                                                        const __half* __restrict__ beta, __half* __restrict__ y, int M,
+                                                        int C, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + warp;
+    if (row >= M) return;
+    const int cv = C / 8;
+    uint4 raw[MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < cv) {
+            raw[i] = *reinterpret_cast<const uint4*>(x + row * C + v * 8);
+            const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_half2(w[t]);
+                sum += f.x + f.y;
+            }
+        }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < cv) {
+            const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_half2(w[t]);
+                sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < cv) {
+            const uint4 gr = *reinterpret_cast<const uint4*>(gamma + v * 8);
+            const uint4 br = *reinterpret_cast<const uint4*>(beta + v * 8);
+            const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+            const uint32_t gw[4] = {gr.x, gr.y, gr.z, gr.w};
+            const uint32_t bw[4] = {br.x, br.y, br.z, br.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_half2(w[t]), gg = unpack_half2(gw[t]), bb = unpack_half2(bw[t]);
+                o[t] = pack_half2((f.x - mean) * rstd * gg.x + bb.x, (f.y - mean) * rstd * gg.y + bb.y);
+            }
+            *reinterpret_cast<uint4*>(y + row * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" size_t gcb_groupnorm_workspace_bytes(int B, int groups) {
+    return (size_t)B * GN_MAX_CHUNKS * groups * 2 * sizeof(float);
+}
+
+extern "C" int gcb_groupnorm_nhwc_fwd(const void* x1, const void* x2, const void* gamma, const void* beta, void* y,
+                                      int B, int HW, int C1, int C2, int groups, float eps, int silu, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    const int C = C1 + C2;
+    GCB_CHECK_ARG(x1 && gamma && beta && y && workspace, "null pointer");
+    GCB_CHECK_ARG(C2 == 0 || x2, "x2 is NULL but C2=%d", C2);
+    GCB_CHECK_ARG(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0, "bad groups=%d for C=%d", groups, C);
+    GCB_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C / groups) % 2 == 0, "channel counts C1=%d C2=%d unsupported", C1, C2);
+    if (workspace_bytes < gcb_groupnorm_workspace_bytes(B, groups)) {
+        gcb_set_error("groupnorm workspace too small");
+        return GCB_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int nchunks = gcb_cdiv(HW, 128);
+    if (nchunks > GN_MAX_CHUNKS) nchunks = GN_MAX_CHUNKS;
+    const int ppc = gcb_cdiv(HW, nchunks);
+    nchunks = gcb_cdiv(HW, ppc);
+    gn_stats_kernel<<<dim3(nchunks, B), 256, 0, st>>>((const __half*)x1, (const __half*)x2, (float*)workspace, HW, C1,
+                                                      C2, groups, ppc);
+    GCB_LAUNCH_CHECK();
+    // apply: ~64 pixels per CTA at C>=1280, more for narrow tensors
+    int pix_per_cta = 16384 / C;
+    if (pix_per_cta < 8) pix_per_cta = 8;
+    const size_t smem = (size_t)C * 2 * sizeof(float);
+    gn_apply_kernel<<<dim3(gcb_cdiv(HW, pix_per_cta), B), 256, smem, st>>>(
+        (const __half*)x1, (const __half*)x2, (const __half*)gamma, (const __half*)beta, (const float*)workspace,
+        (__half*)y, HW, C1, C2, groups, nchunks, pix_per_cta, eps, silu);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
+extern "C" int gcb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int M, int C, float eps,
+                                 void* stream) {
+    GCB_CHECK_ARG(x && gamma && beta && y, "null pointer");
+    GCB_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * 8, "LayerNorm C=%d unsupported (multiple of 8, <= 2048)", C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = gcb_cdiv(M, 8);
+    if (C <= 512)
+        layernorm_kernel<2><<<blocks, 256, 0, st>>>((const __half*)x, (const __half*)gamma, (const __half*)beta,
+                                                    (__half*)y, M, C, eps);
+    else if (C <= 1280)
+        layernorm_kernel<5><<<blocks, 256, 0, st>>>((const __half*)x, (const __half*)gamma, (const __half*)beta,
+                                                    (__half*)y, M, C, eps);
+    else
+        layernorm_kernel<8><<<blocks, 256, 0, st>>>((const __half*)x, (const __half*)gamma, (const __half*)beta,
+                                                    (__half*)y, M, C, eps);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}

@@ -1,0 +1,723 @@
+// 3D-Gaussian rasterisation forward: projection, spherical harmonics, depth ordering, tile binning, compositing.
+// Replaces gsplat 0.1.3's CUDA extension behind gc_model.py:140-154 (project_gaussians), :166 (spherical_harmonics),
+// :174-186 and :191-202 (rasterize_gaussians).  fp32 SIMT, HBM/L2-bound.
+//
+// Binning is NOT gsplat's "sort M 64-bit (tile|depth) keys": the Gaussians (N) are ordered by depth once
+// (4 stable 8-bit radix passes over N 32-bit keys), intersections (M ~ 10 N) are emitted in that order and
+// ONE stable 10-bit radix pass by tile id groups them.  The result is identical to a stable sort by
+// (tile << 32 | depth bits) with ties by Gaussian id - the order the oracle defines - at a fraction of the traffic.
+//
+// Every fp32 expression of the projection kernel is an explicit tree of single IEEE operations (__fmul_rn /
+// __fadd_rn, never contracted to FMA) mirroring oracle/gsplat_ref.py so the result is bit-exact.
+#include "../../include/gaussctrl_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK = 16;
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float rcp(float a) { return __fdiv_rn(1.0f, a); }
+// ((a0*b0 + a1*b1) + a2*b2)
+__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return add(add(mul(a0, b0), mul(a1, b1)), mul(a2, b2));
+}
+__device__ __forceinline__ int f2i_sat(float v) { return __float2int_rz(v); }  // cvt.rzi.s32.f32 saturates, NaN -> 0
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(hi, max(lo, v)); }
+
+struct ProjConst {
+    float vm[12];  // rows 0..2 of the view matrix
+    float pm[16];
+    float fx, fy, cx, cy, lim_x, lim_y, clip, glob_scale, half_w, half_h;
+    int tbx, tby;
+};
+
+__device__ __forceinline__ void tile_bbox(float x, float y, float radius, int tbx, int tby, int& x0, int& x1, int& y0,
+                                          int& y1) {
+    const float blk = (float)BLOCK;
+    const float tcx = __fdiv_rn(x, blk), tcy = __fdiv_rn(y, blk), tr = __fdiv_rn(radius, blk);
+    x0 = clampi(f2i_sat(sub(tcx, tr)), 0, tbx);
+    x1 = clampi(f2i_sat(add(add(tcx, tr), 1.0f)), 0, tbx);
+    y0 = clampi(f2i_sat(sub(tcy, tr)), 0, tby);
+    y1 = clampi(f2i_sat(add(add(tcy, tr), 1.0f)), 0, tby);
+}
+
+__global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ means, const float* __restrict__ scales,
+                                                      const float* __restrict__ quats, const ProjConst P, int N,
+                                                      float* __restrict__ xys, float* __restrict__ depths,
+                                                      int32_t* __restrict__ radii, float* __restrict__ conics,
+                                                      int32_t* __restrict__ nth, float* __restrict__ cov3d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float px = means[3 * i], py = means[3 * i + 1], pz = means[3 * i + 2];
+    const float* vm = P.vm;
+    const float tx = add(dot3(vm[0], px, vm[1], py, vm[2], pz), vm[3]);
+    const float ty = add(dot3(vm[4], px, vm[5], py, vm[6], pz), vm[7]);
+    const float tz = add(dot3(vm[8], px, vm[9], py, vm[10], pz), vm[11]);
+    bool valid = tz > P.clip;
+
+    float w = quats[4 * i], x = quats[4 * i + 1], y = quats[4 * i + 2], z = quats[4 * i + 3];
+    const float inv = rcp(__fsqrt_rn(add(add(add(mul(w, w), mul(x, x)), mul(y, y)), mul(z, z))));
+    w = mul(w, inv);
+    x = mul(x, inv);
+    y = mul(y, inv);
+    z = mul(z, inv);
+    const float r00 = sub(1.0f, mul(2.0f, add(mul(y, y), mul(z, z))));
+    const float r01 = mul(2.0f, sub(mul(x, y), mul(w, z)));
+    const float r02 = mul(2.0f, add(mul(x, z), mul(w, y)));
+    const float r10 = mul(2.0f, add(mul(x, y), mul(w, z)));
+    const float r11 = sub(1.0f, mul(2.0f, add(mul(x, x), mul(z, z))));
+    const float r12 = mul(2.0f, sub(mul(y, z), mul(w, x)));
+    const float r20 = mul(2.0f, sub(mul(x, z), mul(w, y)));
+    const float r21 = mul(2.0f, add(mul(y, z), mul(w, x)));
+    const float r22 = sub(1.0f, mul(2.0f, add(mul(x, x), mul(y, y))));
+    const float sx = mul(P.glob_scale, scales[3 * i]), sy = mul(P.glob_scale, scales[3 * i + 1]),
+                sz = mul(P.glob_scale, scales[3 * i + 2]);
+    const float m00 = mul(r00, sx), m01 = mul(r01, sy), m02 = mul(r02, sz);
+    const float m10 = mul(r10, sx), m11 = mul(r11, sy), m12 = mul(r12, sz);
+    const float m20 = mul(r20, sx), m21 = mul(r21, sy), m22 = mul(r22, sz);
+    const float c00 = dot3(m00, m00, m01, m01, m02, m02);
+    const float c01 = dot3(m00, m10, m01, m11, m02, m12);
+    const float c02 = dot3(m00, m20, m01, m21, m02, m22);
+    const float c11 = dot3(m10, m10, m11, m11, m12, m12);
+    const float c12 = dot3(m10, m20, m11, m21, m12, m22);
+    const float c22 = dot3(m20, m20, m21, m21, m22, m22);
+    if (cov3d) {
+        float* c = cov3d + 6ll * i;
+        c[0] = c00;
+        c[1] = c01;
+        c[2] = c02;
+        c[3] = c11;
+        c[4] = c12;
+        c[5] = c22;
+    }
+    const float tzs = valid ? tz : 1.0f;
+    const float rz = rcp(tzs);
+    const float txc = mul(tzs, fminf(fmaxf(mul(tx, rz), -P.lim_x), P.lim_x));
+    const float tyc = mul(tzs, fminf(fmaxf(mul(ty, rz), -P.lim_y), P.lim_y));
+    const float rz2 = mul(rz, rz);
+    const float j00 = mul(P.fx, rz);
+    const float j02 = mul(mul(-P.fx, txc), rz2);
+    const float j11 = mul(P.fy, rz);
+    const float j12 = mul(mul(-P.fy, tyc), rz2);
+    const float t00 = add(mul(j00, vm[0]), mul(j02, vm[8]));
+    const float t01 = add(mul(j00, vm[1]), mul(j02, vm[9]));
+    const float t02 = add(mul(j00, vm[2]), mul(j02, vm[10]));
+    const float t10 = add(mul(j11, vm[4]), mul(j12, vm[8]));
+    const float t11 = add(mul(j11, vm[5]), mul(j12, vm[9]));
+    const float t12 = add(mul(j11, vm[6]), mul(j12, vm[10]));
+    const float v0x = dot3(t00, c00, t01, c01, t02, c02);
+    const float v0y = dot3(t00, c01, t01, c11, t02, c12);
+    const float v0z = dot3(t00, c02, t01, c12, t02, c22);
+    const float v1x = dot3(t10, c00, t11, c01, t12, c02);
+    const float v1y = dot3(t10, c01, t11, c11, t12, c12);
+    const float v1z = dot3(t10, c02, t11, c12, t12, c22);
+    const float a = add(dot3(v0x, t00, v0y, t01, v0z, t02), 0.3f);
+    const float b = dot3(v0x, t10, v0y, t11, v0z, t12);
+    const float c = add(dot3(v1x, t10, v1y, t11, v1z, t12), 0.3f);
+    const float det = sub(mul(a, c), mul(b, b));
+    valid = valid && (det != 0.0f);
+    const float inv_det = rcp(det != 0.0f ? det : 1.0f);
+    const float con0 = mul(c, inv_det), con1 = mul(-b, inv_det), con2 = mul(a, inv_det);
+    const float b_mid = mul(0.5f, add(a, c));
+    const float disc = __fsqrt_rn(fmaxf(sub(mul(b_mid, b_mid), det), 0.1f));
+    const float v1 = add(b_mid, disc), v2 = sub(b_mid, disc);
+    const float radius = ceilf(mul(3.0f, __fsqrt_rn(fmaxf(v1, v2))));
+    const float* pm = P.pm;
+    const float hx = add(dot3(pm[0], px, pm[1], py, pm[2], pz), pm[3]);
+    const float hy = add(dot3(pm[4], px, pm[5], py, pm[6], pz), pm[7]);
+    const float hw = add(dot3(pm[12], px, pm[13], py, pm[14], pz), pm[15]);
+    const float rw = rcp(add(hw, 1e-6f));
+    const float xs = sub(add(mul(P.half_w, mul(hx, rw)), P.cx), 0.5f);
+    const float ys = sub(add(mul(P.half_h, mul(hy, rw)), P.cy), 0.5f);
+    int x0, x1, y0, y1;
+    tile_bbox(xs, ys, radius, P.tbx, P.tby, x0, x1, y0, y1);
+    const int area = (x1 - x0) * (y1 - y0);
+    valid = valid && area > 0;
+    xys[2 * i] = valid ? xs : 0.f;
+    xys[2 * i + 1] = valid ? ys : 0.f;
+    depths[i] = valid ? tz : 0.f;
+    radii[i] = valid ? f2i_sat(radius) : 0;
+    conics[3 * i] = valid ? con0 : 0.f;
+    conics[3 * i + 1] = valid ? con1 : 0.f;
+    conics[3 * i + 2] = valid ? con2 : 0.f;
+    nth[i] = valid ? area : 0;
+}
+
+// ------------------------------------------------------------------------------------------ spherical harmonics
+__constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                               0.5462742152960396f};
+__constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                               -0.4570457994644658f, 1.445305721320277f,  -0.5900435899266435f};
+
+__device__ __forceinline__ void sh_basis(int degree, float x, float y, float z, float* bas) {
+    bas[0] = 0.28209479177387814f;
+    if (degree < 1) return;
+    const float C1 = 0.4886025119029199f;
+    bas[1] = -C1 * y;
+    bas[2] = C1 * z;
+    bas[3] = -C1 * x;
+    if (degree < 2) return;
+    const float xx = x * x, xy = x * y, xz = x * z, yy = y * y, yz = y * z, zz = z * z;
+    bas[4] = SH_C2[0] * xy;
+    bas[5] = SH_C2[1] * yz;
+    bas[6] = SH_C2[2] * (2.0f * zz - xx - yy);
+    bas[7] = SH_C2[3] * xz;
+    bas[8] = SH_C2[4] * (xx - yy);
+    if (degree < 3) return;
+    bas[9] = SH_C3[0] * y * (3.0f * xx - yy);
+    bas[10] = SH_C3[1] * xy * z;
+    bas[11] = SH_C3[2] * y * (4.0f * zz - xx - yy);
+    bas[12] = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+    bas[13] = SH_C3[4] * x * (4.0f * zz - xx - yy);
+    bas[14] = SH_C3[5] * z * (xx - yy);
+    bas[15] = SH_C3[6] * x * (xx - 3.0f * yy);
+}
+
+// one warp handles 32 Gaussians; coefficient rows (K*3 floats each) are read coalesced through shared memory
+__global__ void __launch_bounds__(256) sh_fwd_kernel(int degree, int K, const float* __restrict__ dirs,
+                                                     const float* __restrict__ coeffs, float* __restrict__ colors, int N) {
+    extern __shared__ float s_co[];  // [8 warps][32][K*3 + 1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = K * 3, ldr = row + 1;
+    float* sw = s_co + warp * 32 * ldr;
+    const long long g0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    if (g0 >= N) return;
+    const int cnt = (int)min(32ll, N - g0);
+    const float* src = coeffs + g0 * row;
+    for (int i = lane; i < cnt * row; i += 32) sw[(i / row) * ldr + i % row] = src[i];
+    __syncwarp();
+    if (lane < cnt) {
+        const long long gi = g0 + lane;
+        float bas[16];
+        sh_basis(degree, dirs[3 * gi], dirs[3 * gi + 1], dirs[3 * gi + 2], bas);
+        const int nb = (degree + 1) * (degree + 1);
+        float r = 0.f, g = 0.f, b = 0.f;
+        const float* c = sw + lane * ldr;
+        for (int k = 0; k < nb; ++k) {
+            r += bas[k] * c[3 * k];
+            g += bas[k] * c[3 * k + 1];
+            b += bas[k] * c[3 * k + 2];
+        }
+        colors[3 * gi] = r;
+        colors[3 * gi + 1] = g;
+        colors[3 * gi + 2] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ scan (int32)
+constexpr int SCAN_T = 1024, SCAN_IPT = 4, SCAN_CHUNK = SCAN_T * SCAN_IPT;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += n;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    const int r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_reduce_kernel(const int* __restrict__ in, int* __restrict__ sums,
+                                                             long long n) {
+    __shared__ int s_warp[33];
+    const long long base = (long long)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
+    int v = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_IPT; ++j)
+        if (base + j < n) v += in[base + j];
+    int total;
+    block_exclusive_scan(v, s_warp, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// out = scan(in) + offsets[block] ; inclusive != 0 -> inclusive scan
+__global__ void __launch_bounds__(SCAN_T) scan_apply_kernel(const int* __restrict__ in, const int* __restrict__ offsets,
+                                                            int* __restrict__ out, long long n, int inclusive) {
+    __shared__ int s_warp[33];
+    const long long base = (long long)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
+    int x[SCAN_IPT];
+    int v = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_IPT; ++j) {
+        x[j] = base + j < n ? in[base + j] : 0;
+        v += x[j];
+    }
+    int total;
+    int run = block_exclusive_scan(v, s_warp, total) + (offsets ? offsets[blockIdx.x] : 0);
+#pragma unroll
+    for (int j = 0; j < SCAN_IPT; ++j) {
+        if (base + j < n) out[base + j] = inclusive ? run + x[j] : run;
+        run += x[j];
+    }
+}
+
+// single block, sequential over chunks: exclusive scan in place (n small)
+__global__ void __launch_bounds__(SCAN_T) scan_small_kernel(int* __restrict__ data, int n) {
+    __shared__ int s_warp[33];
+    int carry = 0;
+    for (int c0 = 0; c0 < n; c0 += SCAN_T) {
+        const int i = c0 + threadIdx.x;
+        const int v = i < n ? data[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, s_warp, total);
+        if (i < n) data[i] = carry + ex;
+        carry += total;
+    }
+}
+
+size_t scan_ws_ints(long long n) {
+    const long long l0 = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    const long long l1 = (l0 + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    return (size_t)(l0 + l1 + 64);
+}
+
+// scan `in` (n ints) to `out` (may alias), exclusive or inclusive
+int scan_i32(const int* in, int* out, long long n, int inclusive, int* ws, cudaStream_t st) {
+    if (n <= 0) return GCB_OK;
+    const long long l0 = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    const long long l1 = (l0 + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    int* s0 = ws;
+    int* s1 = ws + l0;
+    scan_reduce_kernel<<<(unsigned)l0, SCAN_T, 0, st>>>(in, s0, n);
+    if (l0 > SCAN_CHUNK) {
+        scan_reduce_kernel<<<(unsigned)l1, SCAN_T, 0, st>>>(s0, s1, l0);
+        scan_small_kernel<<<1, SCAN_T, 0, st>>>(s1, (int)l1);
+        scan_apply_kernel<<<(unsigned)l1, SCAN_T, 0, st>>>(s0, s1, s0, l0, 0);
+    } else {
+        scan_small_kernel<<<1, SCAN_T, 0, st>>>(s0, (int)l0);
+    }
+    scan_apply_kernel<<<(unsigned)l0, SCAN_T, 0, st>>>(in, s0, out, n, inclusive);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ stable radix pass
+constexpr int RP_WARPS = 8, RP_PER_WARP = 1024, RP_PER_BLOCK = RP_WARPS * RP_PER_WARP, RP_MAX_BINS = 1024;
+
+__device__ __forceinline__ void rp_count(const uint32_t* __restrict__ keys, long long n, int shift, uint32_t mask,
+                                         int* cnt_w) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w0 = (long long)blockIdx.x * RP_PER_BLOCK + (long long)warp * RP_PER_WARP;
+    for (int it = 0; it < RP_PER_WARP / 32; ++it) {
+        const long long i = w0 + it * 32 + lane;
+        const bool act = i < n;
+        const unsigned am = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const uint32_t bin = (keys[i] >> shift) & mask;
+            const unsigned peers = __match_any_sync(am, bin);
+            if ((peers & ((1u << lane) - 1)) == 0) cnt_w[bin] += __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) rp_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift,
+                                                      int bins, int* __restrict__ counts) {
+    extern __shared__ int s_cnt[];  // [RP_WARPS][bins]
+    for (int i = threadIdx.x; i < RP_WARPS * bins; i += 256) s_cnt[i] = 0;
+    __syncthreads();
+    rp_count(keys, n, shift, (uint32_t)bins - 1, s_cnt + (threadIdx.x >> 5) * bins);
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += 256) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < RP_WARPS; ++w) t += s_cnt[w * bins + b];
+        counts[(long long)b * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) rp_scatter_kernel(const uint32_t* __restrict__ keys,
+                                                         const int32_t* __restrict__ vals, long long n, int shift,
+                                                         int bins, const int* __restrict__ offsets,
+                                                         uint32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
+    extern __shared__ int s_cnt[];  // [RP_WARPS][bins] -> running write positions
+    for (int i = threadIdx.x; i < RP_WARPS * bins; i += 256) s_cnt[i] = 0;
+    __syncthreads();
+    const uint32_t mask = (uint32_t)bins - 1;
+    rp_count(keys, n, shift, mask, s_cnt + (threadIdx.x >> 5) * bins);
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += 256) {
+        int run = offsets[(long long)b * gridDim.x + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RP_WARPS; ++w) {
+            const int c = s_cnt[w * bins + b];
+            s_cnt[w * bins + b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* pos_w = s_cnt + warp * bins;
+    const long long w0 = (long long)blockIdx.x * RP_PER_BLOCK + (long long)warp * RP_PER_WARP;
+    for (int it = 0; it < RP_PER_WARP / 32; ++it) {
+        const long long i = w0 + it * 32 + lane;
+        const bool act = i < n;
+        const unsigned am = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const uint32_t key = keys[i];
+            const uint32_t bin = (key >> shift) & mask;
+            const unsigned peers = __match_any_sync(am, bin);
+            const int rank = __popc(peers & ((1u << lane) - 1));
+            const int pos = pos_w[bin] + rank;
+            __syncwarp(am);
+            if (rank == 0) pos_w[bin] += __popc(peers);
+            if (keys_out) keys_out[pos] = key;
+            vals_out[pos] = vals ? vals[i] : (int32_t)i;
+        }
+        __syncwarp();
+    }
+}
+
+inline long long rp_blocks(long long n) { return (n + RP_PER_BLOCK - 1) / RP_PER_BLOCK; }
+
+// one stable pass; ws_counts must hold bins * blocks ints followed by scan workspace
+int radix_pass(const uint32_t* keys, const int32_t* vals, long long n, int shift, int bits, uint32_t* keys_out,
+               int32_t* vals_out, int* ws, cudaStream_t st) {
+    const int bins = 1 << bits;
+    const long long nb = rp_blocks(n);
+    const size_t smem = (size_t)RP_WARPS * bins * sizeof(int);
+    int* counts = ws;
+    int* scan_ws = ws + (long long)bins * nb;
+    rp_hist_kernel<<<(unsigned)nb, 256, smem, st>>>(keys, n, shift, bins, counts);
+    int rc = scan_i32(counts, counts, (long long)bins * nb, 0, scan_ws, st);
+    if (rc != GCB_OK) return rc;
+    rp_scatter_kernel<<<(unsigned)nb, 256, smem, st>>>(keys, vals, n, shift, bins, counts, keys_out, vals_out);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
+size_t radix_ws_ints(long long n, int bits) {
+    const long long cnt = (long long)(1 << bits) * rp_blocks(n);
+    return (size_t)cnt + scan_ws_ints(cnt);
+}
+
+__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx,
+                                  int32_t* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+// emit intersections of the depth-ordered Gaussians: tile ids (as radix keys) and Gaussian ids
+__global__ void emit_isects_kernel(const float* __restrict__ xys, const int32_t* __restrict__ radii,
+                                   const int32_t* __restrict__ sorted_ids, const int32_t* __restrict__ cum_sorted, int N,
+                                   int tbx, int tby, uint32_t* __restrict__ tile_of, int32_t* __restrict__ gid_of) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int g = sorted_ids[i];
+    const int rad = radii[g];
+    if (rad <= 0) return;
+    int x0, x1, y0, y1;
+    tile_bbox(xys[2 * g], xys[2 * g + 1], (float)rad, tbx, tby, x0, x1, y0, y1);
+    long long cur = i > 0 ? cum_sorted[i - 1] : 0;
+    for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) {
+            tile_of[cur] = (uint32_t)(ty * tbx + tx);
+            gid_of[cur] = g;
+            ++cur;
+        }
+}
+
+__global__ void tile_bins_kernel(const uint32_t* __restrict__ tile_sorted, long long M, int32_t* __restrict__ bins) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const uint32_t t = tile_sorted[i];
+    if (i == 0 || tile_sorted[i - 1] != t) bins[2 * t] = (int32_t)i;
+    if (i == M - 1 || tile_sorted[i + 1] != t) bins[2 * t + 1] = (int32_t)(i + 1);
+}
+
+__global__ void isect_keys_kernel(const uint32_t* __restrict__ tile_sorted, const int32_t* __restrict__ gids,
+                                  const float* __restrict__ depths, long long M, int64_t* __restrict__ keys) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    keys[i] = ((int64_t)tile_sorted[i] << 32) | (int64_t)(uint32_t)__float_as_uint(depths[gids[i]]);
+}
+
+// ------------------------------------------------------------------------------------------ compositing
+template <int C>
+__global__ void __launch_bounds__(256) rasterize_fwd_kernel(const float* __restrict__ xys,
+                                                            const float* __restrict__ conics,
+                                                            const float* __restrict__ colors,
+                                                            const float* __restrict__ opac,
+                                                            const int32_t* __restrict__ gids,
+                                                            const int32_t* __restrict__ bins, int H, int W, int tbx,
+                                                            float bg0, float bg1, float bg2, float bg3,
+                                                            float* __restrict__ out, float* __restrict__ final_T,
+                                                            int32_t* __restrict__ final_idx) {
+    __shared__ float4 s_xyo[256];   // x, y, opacity, conic.x
+    __shared__ float2 s_con[256];   // conic.y, conic.z
+    __shared__ float s_col[256 * C];
+    const int tile = blockIdx.y * tbx + blockIdx.x;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int px_i = blockIdx.x * BLOCK + tx, py_i = blockIdx.y * BLOCK + ty;
+    const bool inside = px_i < W && py_i < H;
+    const float px = (float)px_i, py = (float)py_i;
+    const int start = bins[2 * tile], end = bins[2 * tile + 1];
+    float T = 1.f;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    int last = 0;
+    bool done = !inside;
+    for (int b0 = start; b0 < end; b0 += 256) {
+        if (__syncthreads_and(done)) break;
+        const int i = b0 + threadIdx.x;
+        if (i < end) {
+            const int g = gids[i];
+            const float2 xy = reinterpret_cast<const float2*>(xys)[g];
+            s_xyo[threadIdx.x] = make_float4(xy.x, xy.y, opac[g], conics[3 * g]);
+            s_con[threadIdx.x] = make_float2(conics[3 * g + 1], conics[3 * g + 2]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) s_col[threadIdx.x * C + c] = colors[(long long)g * C + c];
+        }
+        __syncthreads();
+        const int cnt = min(256, end - b0);
+        if (!done) {
+            for (int j = 0; j < cnt; ++j) {
+                const float4 q = s_xyo[j];
+                const float2 cc = s_con[j];
+                const float dx = q.x - px, dy = q.y - py;
+                const float sigma = 0.5f * (q.w * dx * dx + cc.y * dy * dy) + cc.x * dx * dy;
+                const float alpha = fminf(0.999f, q.z * expf(-sigma));
+                if (sigma < 0.f || alpha < (1.f / 255.f)) continue;
+                const float nT = T * (1.f - alpha);
+                if (nT <= 1e-4f) {
+                    done = true;
+                    break;
+                }
+                const float vis = alpha * T;
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] += vis * s_col[j * C + c];
+                T = nT;
+                last = b0 + j;
+            }
+        }
+    }
+    if (inside) {
+        const long long pid = (long long)py_i * W + px_i;
+        const float bg[4] = {bg0, bg1, bg2, bg3};
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[pid * C + c] = acc[c] + T * bg[c];
+        final_T[pid] = T;
+        final_idx[pid] = last;
+    }
+}
+
+__global__ void raster_finalize_kernel(const float* __restrict__ img4, const float* __restrict__ final_T,
+                                       float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ alpha,
+                                       int HW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const float4 v = reinterpret_cast<const float4*>(img4)[i];
+    const float a = 1.f - final_T[i];
+    rgb[3 * i] = fminf(v.x, 1.f);
+    rgb[3 * i + 1] = fminf(v.y, 1.f);
+    rgb[3 * i + 2] = fminf(v.z, 1.f);
+    depth[i] = a > 0.f ? v.w / a : 1000.f;
+    alpha[i] = a;
+}
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" int gcb_project_gaussians_fwd(const float* means3d, const float* scales, float glob_scale, const float* quats,
+                                         const float* h_viewmat, const float* h_projmat, float fx, float fy, float cx,
+                                         float cy, int img_h, int img_w, int tile_bx, int tile_by, float clip_thresh,
+                                         int N, float* xys, float* depths, int32_t* radii, float* conics,
+                                         int32_t* num_tiles_hit, float* cov3d, void* stream) {
+    GCB_CHECK_ARG(means3d && scales && quats && h_viewmat && h_projmat, "null input");
+    GCB_CHECK_ARG(xys && depths && radii && conics && num_tiles_hit, "null output");
+    GCB_CHECK_ARG(N >= 0, "N < 0");
+    if (N == 0) return GCB_OK;
+    ProjConst P;
+    for (int i = 0; i < 12; ++i) P.vm[i] = h_viewmat[i];
+    for (int i = 0; i < 16; ++i) P.pm[i] = h_projmat[i];
+    P.fx = fx;
+    P.fy = fy;
+    P.cx = cx;
+    P.cy = cy;
+    // float32(1.3) * float32(0.5 * W / fx), evaluated like the oracle
+    P.lim_x = 1.3f * (float)(0.5 * (double)img_w / (double)fx);
+    P.lim_y = 1.3f * (float)(0.5 * (double)img_h / (double)fy);
+    P.clip = clip_thresh;
+    P.glob_scale = glob_scale;
+    P.half_w = 0.5f * (float)img_w;
+    P.half_h = 0.5f * (float)img_h;
+    P.tbx = tile_bx;
+    P.tby = tile_by;
+    project_kernel<<<gcb_cdiv(N, 256), 256, 0, ST>>>(means3d, scales, quats, P, N, xys, depths, radii, conics,
+                                                     num_tiles_hit, cov3d);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
+extern "C" int gcb_sh_fwd(int degree, int K, const float* viewdirs, const float* coeffs, float* colors, int N,
+                          void* stream) {
+    GCB_CHECK_ARG(viewdirs && coeffs && colors, "null pointer");
+    GCB_CHECK_ARG(degree >= 0 && degree <= 3 && K >= (degree + 1) * (degree + 1) && K <= 16, "bad degree=%d / K=%d",
+                  degree, K);
+    if (N == 0) return GCB_OK;
+    const size_t smem = (size_t)8 * 32 * (K * 3 + 1) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        GCB_CUDA(cudaFuncSetAttribute(sh_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured = true;
+    }
+    sh_fwd_kernel<<<gcb_cdiv(N, 256), 256, smem, ST>>>(degree, K, viewdirs, coeffs, colors, N);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
+extern "C" size_t gcb_scan_workspace_bytes(int N) { return scan_ws_ints(N) * sizeof(int); }
+
+extern "C" int gcb_cumsum_i32(const int32_t* in, int32_t* out, int N, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    GCB_CHECK_ARG(in && out && workspace, "null pointer");
+    if (workspace_bytes < gcb_scan_workspace_bytes(N)) {
+        gcb_set_error("scan workspace too small");
+        return GCB_ERR_WORKSPACE;
+    }
+    return scan_i32(in, out, N, 1, (int*)workspace, ST);
+}
+
+// workspace layout of gcb_depth_order: keys A/B [N] u32, ids B [N] i32, nth_sorted [N] i32, radix/scan scratch
+extern "C" size_t gcb_depth_order_workspace_bytes(int N) {
+    return ((size_t)4 * N + radix_ws_ints(N, 8) + scan_ws_ints(N) + 64) * sizeof(int);
+}
+
+extern "C" int gcb_depth_order(const float* depths, const int32_t* num_tiles_hit, int N, int32_t* sorted_ids,
+                               int32_t* cum_sorted, void* workspace, size_t workspace_bytes, void* stream) {
+    GCB_CHECK_ARG(depths && num_tiles_hit && sorted_ids && cum_sorted && workspace, "null pointer");
+    GCB_CHECK_ARG(N > 0, "N must be positive");
+    if (workspace_bytes < gcb_depth_order_workspace_bytes(N)) {
+        gcb_set_error("depth-order workspace too small");
+        return GCB_ERR_WORKSPACE;
+    }
+    uint32_t* kA = (uint32_t*)workspace;
+    uint32_t* kB = kA + N;
+    int32_t* vB = (int32_t*)(kB + N);
+    int32_t* nth_sorted = vB + N;
+    int* scratch = (int*)(nth_sorted + N);
+    // depths are >= 0 so their bit patterns order like unsigned integers; 4 stable LSD passes of 8 bits
+    const uint32_t* dk = reinterpret_cast<const uint32_t*>(depths);
+    int rc;
+    if ((rc = radix_pass(dk, nullptr, N, 0, 8, kA, sorted_ids, scratch, ST))) return rc;
+    if ((rc = radix_pass(kA, sorted_ids, N, 8, 8, kB, vB, scratch, ST))) return rc;
+    if ((rc = radix_pass(kB, vB, N, 16, 8, kA, sorted_ids, scratch, ST))) return rc;
+    if ((rc = radix_pass(kA, sorted_ids, N, 24, 8, kB, vB, scratch, ST))) return rc;
+    GCB_CUDA(cudaMemcpyAsync(sorted_ids, vB, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToDevice, ST));
+    gather_i32_kernel<<<gcb_cdiv(N, 256), 256, 0, ST>>>(num_tiles_hit, sorted_ids, nth_sorted, N);
+    return scan_i32(nth_sorted, cum_sorted, N, 1, scratch, ST);
+}
+
+extern "C" size_t gcb_bin_tiles_workspace_bytes(int N, long long M, int tile_bx, int tile_by) {
+    (void)N;
+    (void)tile_bx;
+    (void)tile_by;
+    return ((size_t)3 * M + radix_ws_ints(M, 10) + 64) * sizeof(int);
+}
+
+extern "C" int gcb_bin_tiles(const float* xys, const float* depths, const int32_t* radii, const int32_t* sorted_ids,
+                             const int32_t* cum_sorted, int N, long long M, int tile_bx, int tile_by,
+                             int32_t* gaussian_ids, int32_t* tile_bins, int64_t* isect_keys, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+    GCB_CHECK_ARG(xys && radii && sorted_ids && cum_sorted && gaussian_ids && tile_bins && workspace, "null pointer");
+    GCB_CHECK_ARG(!isect_keys || depths, "isect_keys requested without depths");
+    const int ntiles = tile_bx * tile_by;
+    GCB_CHECK_ARG(ntiles > 0 && ntiles <= (1 << 20), "tile grid %dx%d unsupported", tile_bx, tile_by);
+    GCB_CHECK_ARG(M >= 0 && M < (1ll << 31), "M out of range");
+    GCB_CUDA(cudaMemsetAsync(tile_bins, 0, (size_t)ntiles * 2 * sizeof(int32_t), ST));
+    if (M == 0) return GCB_OK;
+    if (workspace_bytes < gcb_bin_tiles_workspace_bytes(N, M, tile_bx, tile_by)) {
+        gcb_set_error("bin-tiles workspace too small");
+        return GCB_ERR_WORKSPACE;
+    }
+    uint32_t* tA = (uint32_t*)workspace;
+    uint32_t* tB = tA + M;
+    int32_t* gA = (int32_t*)(tB + M);
+    int* scratch = (int*)(gA + M);
+    emit_isects_kernel<<<gcb_cdiv(N, 256), 256, 0, ST>>>(xys, radii, sorted_ids, cum_sorted, N, tile_bx, tile_by, tA, gA);
+    GCB_LAUNCH_CHECK();
+    int bits_total = 1;
+    while ((1 << bits_total) < ntiles) ++bits_total;
+    int rc;
+    const uint32_t* tile_sorted;
+    if (bits_total <= 10) {
+        if ((rc = radix_pass(tA, gA, M, 0, bits_total, tB, gaussian_ids, scratch, ST))) return rc;
+        tile_sorted = tB;
+    } else {
+        const int lo = bits_total / 2, hi = bits_total - lo;
+        if ((rc = radix_pass(tA, gA, M, 0, lo, tB, gaussian_ids, scratch, ST))) return rc;
+        if ((rc = radix_pass(tB, gaussian_ids, M, lo, hi, tA, gA, scratch, ST))) return rc;
+        GCB_CUDA(cudaMemcpyAsync(gaussian_ids, gA, (size_t)M * sizeof(int32_t), cudaMemcpyDeviceToDevice, ST));
+        tile_sorted = tA;
+    }
+    const unsigned nb = (unsigned)((M + 255) / 256);
+    tile_bins_kernel<<<nb, 256, 0, ST>>>(tile_sorted, M, tile_bins);
+    if (isect_keys) isect_keys_kernel<<<nb, 256, 0, ST>>>(tile_sorted, gaussian_ids, depths, M, isect_keys);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
+extern "C" int gcb_rasterize_fwd(const float* xys, const float* conics, const float* colors, const float* opacities,
+                                 const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
+                                 const float* h_background, float* out_img, float* final_T, int32_t* final_idx,
+                                 void* stream) {
+    GCB_CHECK_ARG(xys && conics && colors && opacities && gaussian_ids && tile_bins, "null input");
+    GCB_CHECK_ARG(out_img && final_T && final_idx && h_background, "null output/background");
+    const int tbx = gcb_cdiv(img_w, BLOCK), tby = gcb_cdiv(img_h, BLOCK);
+    dim3 grid(tbx, tby);
+    float bg[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C && c < 4; ++c) bg[c] = h_background[c];
+    switch (C) {
+        case 1:
+            rasterize_fwd_kernel<1><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins, img_h,
+                                                          img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img, final_T,
+                                                          final_idx);
+            break;
+        case 3:
+            rasterize_fwd_kernel<3><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins, img_h,
+                                                          img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img, final_T,
+                                                          final_idx);
+            break;
+        case 4:
+            rasterize_fwd_kernel<4><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins, img_h,
+                                                          img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img, final_T,
+                                                          final_idx);
+            break;
+        default:
+            gcb_set_error("rasterize: C=%d not built (1, 3, 4)", C);
+            return GCB_ERR_UNSUPPORTED;
+    }
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
+extern "C" int gcb_raster_finalize(const float* img4, const float* final_T, float* rgb, float* depth, float* alpha,
+                                   int HW, void* stream) {
+    GCB_CHECK_ARG(img4 && final_T && rgb && depth && alpha, "null pointer");
+    raster_finalize_kernel<<<gcb_cdiv(HW, 256), 256, 0, ST>>>(img4, final_T, rgb, depth, alpha, HW);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}

@@ -1,0 +1,197 @@
+"""Denoising loops of the hot path on device tensors: DDIM inversion (render_reverse's `pipe(...)` call,
+gaussctrl/gc_pipeline.py:141-145) and cross-view-attention editing (edit_images' `pipe(...)` call, :206-219).
+
+Two edit schedules produce the same latents (reference-view rows never depend on chunk-view rows):
+  * "reference"  - the reference's own: every chunk denoises [R refs + c views] together, refs recomputed per chunk;
+  * "refs_once"  - B200-first: per DDIM step the R reference views are denoised once (their per-layer K/V recorded),
+                   then every other view batch reads that K/V; 2.3x fewer network evaluations at R=4, c=3, and
+                   view batches become independent (this is what shards across GPUs, see parallel.py).
+Each step's network evaluation + CFG combine + DDIM update is captured in a CUDA graph and replayed per step
+(timestep and scheduler coefficients live in device buffers)."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .diffusion import (AttnPlan, SD15Denoiser, cached_crossview_plan, literal_crossview_plan, vanilla_plan)
+from .sd15_spec import DDIMTables
+
+
+class _GraphedStep:
+    """One denoising step for a fixed batch shape as a CUDA graph: x <- ddim(x, eps(x, t, cond))."""
+
+    def __init__(self, den: SD15Denoiser, n_lat: int, cfg: bool, guidance: float, plan: AttnPlan, hw: int,
+                 use_graph: bool):
+        dev = den.dev
+        self.den, self.cfg, self.guidance, self.plan, self.n_lat = den, cfg, guidance, plan, n_lat
+        B = 2 * n_lat if cfg else n_lat
+        self.x = torch.zeros((n_lat, hw, hw, 4), dtype=torch.float16, device=dev)
+        self.cond = torch.zeros((B, hw, hw, den.ch[0]), dtype=torch.float16, device=dev)
+        self.t = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self.coef = torch.zeros((4,), dtype=torch.float32, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = use_graph
+        self.launches = 0
+
+    def _body(self) -> None:
+        n = self.n_lat
+        xin = torch.cat([self.x, self.x], dim=0) if self.cfg else self.x
+        eps = self.den.eps(xin, self.t, self.cond, self.plan)
+        if self.cfg:
+            ops.cfg_ddim_step(eps[:n], eps[n:], self.x, self.guidance, self.coef, out=self.x)
+        else:
+            ops.cfg_ddim_step(eps, None, self.x, 0.0, self.coef, out=self.x)
+
+    def set_cond(self, cond_emb: torch.Tensor) -> None:
+        """cond_emb [n_lat, hw, hw, C0] (the conditioning image is the same for both CFG halves)."""
+        n = self.n_lat
+        self.cond[:n].copy_(cond_emb)
+        if self.cfg:
+            self.cond[n:].copy_(cond_emb)
+
+    def run(self, t: int, coefs: Sequence[float]) -> None:
+        self.t.fill_(float(t))
+        self.coef.copy_(torch.tensor(coefs, dtype=torch.float32), non_blocking=False)
+        if not self.use_graph:
+            self._body()
+            return
+        if self.graph is None:
+            l0 = ops.LAUNCHES[0]
+            x_save = self.x.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()  # warm-up outside capture (lazy packing of weights, cudaFuncSetAttribute calls)
+            torch.cuda.current_stream().wait_stream(s)
+            self.launches = ops.LAUNCHES[0] - l0
+            self.x.copy_(x_save)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.x.copy_(x_save)
+        else:
+            ops.LAUNCHES[0] += self.launches
+        self.graph.replay()
+
+
+class EditEngine:
+    def __init__(self, denoiser: SD15Denoiser, tables: Optional[DDIMTables] = None, use_graphs: bool = True):
+        self.den = denoiser
+        self.dev = denoiser.dev
+        self.tables = tables or DDIMTables()
+        self.use_graphs = use_graphs
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _latents_in(self, z_nchw: torch.Tensor) -> torch.Tensor:
+        return ops.nchw_to_nhwc(z_nchw.to(device=self.dev, dtype=torch.float16).contiguous())
+
+    def _cond_emb(self, disparity_nchw: torch.Tensor, batch: int = 8) -> torch.Tensor:
+        """[V,3,H,W] disparity images -> ControlNet conditioning embeddings [V,h,w,C0] (step-invariant)."""
+        outs = []
+        for i in range(0, disparity_nchw.shape[0], batch):
+            d = ops.nchw_to_nhwc(disparity_nchw[i:i + batch].to(device=self.dev, dtype=torch.float16).contiguous())
+            outs.append(self.den.controlnet_cond(d))
+        return torch.cat(outs, dim=0)
+
+    # ------------------------------------------------------------------------------------------ inversion
+    @torch.no_grad()
+    def invert(self, z0: torch.Tensor, disparity: torch.Tensor, prompt_embed: torch.Tensor, S: int,
+               batch: int = 8) -> torch.Tensor:
+        """DDIM inversion of V views (gc_pipeline.py:141-145: guidance_scale=0 => no CFG, vanilla attention).
+        z0 [V,4,h,w], disparity [V,3,H,W], prompt_embed [1,77,768] -> z_T [V,4,h,w] fp16.
+        Views are independent, so they are batched `batch` at a time instead of the reference's batch 1."""
+        V, hw = z0.shape[0], z0.shape[-1]
+        self.den.set_prompts(prompt_embed)
+        cond = self._cond_emb(disparity)
+        x_all = self._latents_in(z0)
+        out = torch.empty_like(x_all)
+        steps: Dict[int, _GraphedStep] = {}
+        ts = self.tables.inverse_timesteps(S)
+        for i in range(0, V, batch):
+            n = min(batch, V - i)
+            if n not in steps:
+                steps[n] = _GraphedStep(self.den, n, False, 0.0, vanilla_plan(n, self.dev), hw, self.use_graphs)
+            st = steps[n]
+            st.x.copy_(x_all[i:i + n])
+            st.set_cond(cond[i:i + n])
+            for t in ts:
+                st.run(t, self.tables.inverse_step_coefs(t, S))
+            out[i:i + n].copy_(st.x)
+        return ops.nhwc_to_nchw(out)
+
+    # ------------------------------------------------------------------------------------------ editing
+    @torch.no_grad()
+    def edit_reference_schedule(self, latents: torch.Tensor, disparity: torch.Tensor, pos_embed: torch.Tensor,
+                                neg_embed: torch.Tensor, S: int, guidance: float, num_ref: int,
+                                ref_frames: Sequence[int] = (0, 1, 2, 3)) -> torch.Tensor:
+        """One `pipe(...)` call of edit_images exactly as the reference batches it (gc_pipeline.py:206-219):
+        latents [F,4,h,w] = [refs | chunk], CFG rows [uncond x F | cond x F].  Returns the final latents of the
+        chunk rows [F-num_ref,4,h,w] (decode is the VAE's job)."""
+        assert guidance > 1.0, "the reference assumes CFG doubling (utils.py:94)"
+        F, hw = latents.shape[0], latents.shape[-1]
+        self.den.set_prompts(torch.cat([neg_embed, pos_embed], dim=0))
+        st = _GraphedStep(self.den, F, True, guidance, literal_crossview_plan(F, self.dev, ref_frames), hw,
+                          self.use_graphs)
+        st.x.copy_(self._latents_in(latents))
+        st.set_cond(self._cond_emb(disparity))
+        for t in self.tables.timesteps(S):
+            st.run(t, self.tables.step_coefs(t, S))
+        return ops.nhwc_to_nchw(st.x[num_ref:].contiguous())
+
+    @torch.no_grad()
+    def edit_refs_once(self, latents: torch.Tensor, disparity: torch.Tensor, ref_indices: Sequence[int],
+                       pos_embed: torch.Tensor, neg_embed: torch.Tensor, S: int, guidance: float, view_batch: int = 4,
+                       ref_frames: Sequence[int] = (0, 1, 2, 3), view_ids: Optional[Sequence[int]] = None,
+                       ref_exchange: Optional[Callable] = None) -> torch.Tensor:
+        """Edit all V views: latents [V,4,h,w] (z_T of every view), disparity [V,3,H,W], ref_indices = the R reference
+        view ids.  Per DDIM step: (1) the R references are denoised once, recording every self-attention layer's
+        K/V; (2) the remaining views are denoised in batches of `view_batch`, reading that K/V.
+        Reference views' own edited latents are rows of pass (1) (SURVEY §8a gotcha 6).
+        `view_ids`: the subset of views this rank edits (multi-GPU sharding); default all."""
+        assert guidance > 1.0
+        V, hw = latents.shape[0], latents.shape[-1]
+        R = len(ref_indices)
+        ids = list(range(V)) if view_ids is None else list(view_ids)
+        non_ref = [v for v in ids if v not in set(ref_indices)]
+        self.den.set_prompts(torch.cat([neg_embed, pos_embed], dim=0))
+        x_all = self._latents_in(latents)
+        need = sorted(set(non_ref) | set(ref_indices))
+        cond_map = {v: c for v, c in zip(need, self._cond_emb(disparity[need]))}
+        # (1) reference pass
+        rec: Dict[str, torch.Tensor] = {}
+        ref_step = _GraphedStep(self.den, R, True, guidance,
+                                literal_crossview_plan(R, self.dev, ref_frames, record_kv=rec), hw, self.use_graphs)
+        ref_step.x.copy_(x_all[list(ref_indices)])
+        ref_step.set_cond(torch.stack([cond_map[v] for v in ref_indices]))
+        # (2) view batches (the last one is padded by repeating its final view so one graph serves all)
+        batches: List[List[int]] = [non_ref[i:i + view_batch] for i in range(0, len(non_ref), view_batch)]
+        bsz = min(view_batch, max(1, len(non_ref)))
+        view_step: Optional[_GraphedStep] = None
+        x_views: List[torch.Tensor] = []
+        conds: List[torch.Tensor] = []
+        for b in batches:
+            padded = b + [b[-1]] * (bsz - len(b))
+            x_views.append(x_all[padded].clone())
+            conds.append(torch.stack([cond_map[v] for v in padded]))
+        for t in self.tables.timesteps(S):
+            coefs = self.tables.step_coefs(t, S)
+            ref_step.run(t, coefs)
+            if ref_exchange is not None:
+                ref_exchange(rec)
+            if batches and view_step is None:
+                view_step = _GraphedStep(self.den, bsz, True, guidance,
+                                         cached_crossview_plan(bsz, R, self.dev, rec, ref_frames), hw, self.use_graphs)
+            for bi in range(len(batches)):
+                view_step.x.copy_(x_views[bi])
+                view_step.set_cond(conds[bi])
+                view_step.run(t, coefs)
+                x_views[bi].copy_(view_step.x)
+        out = torch.zeros_like(x_all)
+        for ri, v in enumerate(ref_indices):
+            out[v].copy_(ref_step.x[ri])
+        for b, xv in zip(batches, x_views):
+            for j, v in enumerate(b):
+                out[v].copy_(xv[j])
+        return ops.nhwc_to_nchw(out)

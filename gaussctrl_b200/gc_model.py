@@ -1,0 +1,131 @@
+"""GaussCtrlModel on the sm_100a rasteriser: mirror of gaussctrl/gc_model.py:39-221.
+
+`get_outputs(camera)` keeps the reference's contract - returns {"rgb" [H,W,3], "depth" [H,W,1], "accumulation"
+[H,W,1]} fp32 and sets `self.xys`, `self.radii`, `self.last_size` - but in eval mode runs ONE binning and ONE fused
+4-channel (r,g,b,depth) composite instead of the reference's two bin+sort+rasterize passes (gc_model.py:174-202)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Type, Union
+
+import torch
+
+from . import gsplat_ops
+from ._compat import Cameras, SplatfactoModel, SplatfactoModelConfig
+
+
+def projection_matrix(znear: float, zfar: float, fovx: float, fovy: float, device="cpu") -> torch.Tensor:
+    """nerfstudio 1.0.0 splatfacto.projection_matrix (called at gc_model.py:115)."""
+    t = znear * math.tan(0.5 * fovy)
+    b = -t
+    r = znear * math.tan(0.5 * fovx)
+    l = -r
+    n, f = znear, zfar
+    return torch.tensor([[2 * n / (r - l), 0.0, (r + l) / (r - l), 0.0],
+                         [0.0, 2 * n / (t - b), (t + b) / (t - b), 0.0],
+                         [0.0, 0.0, (f + n) / (f - n), -1.0 * f * n / (f - n)],
+                         [0.0, 0.0, 1.0, 0.0]], dtype=torch.float32, device=device)
+
+
+def viewmat_from_c2w(c2w: torch.Tensor) -> torch.Tensor:
+    """gc_model.py:97-107: flip y/z, analytic rigid inverse.  Tiny host-side 4x4 math."""
+    c2w = c2w.detach().to("cpu", torch.float32)
+    R = c2w[:3, :3] @ torch.diag(torch.tensor([1.0, -1.0, -1.0]))
+    T = c2w[:3, 3:4]
+    vm = torch.eye(4)
+    vm[:3, :3] = R.T
+    vm[:3, 3:4] = -R.T @ T
+    return vm
+
+
+def render_gaussians(params: Dict[str, torch.Tensor], c2w: torch.Tensor, fx, fy, cx, cy, H: int, W: int,
+                     sh_degree_active: int, background: torch.Tensor, training: bool = False,
+                     state: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    """Functional core of get_outputs (gc_model.py:95-206) for one camera.  params are CUDA tensors under the
+    splatfacto names; c2w is the [3,4]/[4,4] camera-to-world matrix."""
+    means = params["means"]
+    dev = means.device
+    vm = viewmat_from_c2w(c2w)
+    fovx = 2 * math.atan(W / (2 * fx))
+    fovy = 2 * math.atan(H / (2 * fy))
+    pm = projection_matrix(0.001, 1000, fovx, fovy)
+    tile_bounds = ((W + 15) // 16, (H + 15) // 16, 1)
+    quats = params["quats"]
+    colors = torch.cat((params["features_dc"][:, None, :], params["features_rest"]), dim=1)
+    xys, depths, radii, conics, nth, _ = gsplat_ops.project_gaussians(
+        means, torch.exp(params["scales"]), 1, quats / quats.norm(dim=-1, keepdim=True), vm[:3, :], pm @ vm, fx, fy, cx,
+        cy, H, W, tile_bounds)
+    if state is not None:
+        state["xys"], state["radii"] = xys, radii
+    if int(radii.sum().item()) == 0:
+        return {"rgb": background.repeat(H, W, 1)}
+    if sh_degree_active >= 0 and colors.shape[1] > 1:
+        viewdirs = means.detach() - c2w.detach().to(dev, torch.float32)[:3, 3]
+        viewdirs = viewdirs / viewdirs.norm(dim=-1, keepdim=True)
+        rgbs = torch.clamp(gsplat_ops.spherical_harmonics(sh_degree_active, viewdirs, colors) + 0.5, min=0.0)
+    else:
+        rgbs = torch.sigmoid(colors[:, 0, :])
+    opac = torch.sigmoid(params["opacities"])
+    if training:
+        rgb, alpha = gsplat_ops.rasterize_gaussians(xys, depths, radii, conics, nth, rgbs, opac, H, W,
+                                                    background=background, return_alpha=True)
+        return {"rgb": torch.clamp(rgb, max=1.0), "depth": None, "accumulation": alpha[..., None]}
+    rgb, depth, alpha = gsplat_ops.rasterize_rgbd(xys, depths, radii, conics, nth, rgbs, opac, H, W, background)
+    return {"rgb": rgb, "depth": depth, "accumulation": alpha}
+
+
+@dataclass
+class GaussCtrlModelConfig(SplatfactoModelConfig):
+    """Same fields/defaults as gaussctrl/gc_model.py:39-50."""
+    _target: Type = field(default_factory=lambda: GaussCtrlModel)
+    use_lpips: bool = True
+    use_l1: bool = True
+    patch_size: int = 32
+    lpips_loss_mult: float = 1.0
+
+
+class GaussCtrlModel(SplatfactoModel):
+    config: GaussCtrlModelConfig
+
+    def get_outputs(self, camera: Cameras) -> Dict[str, Union[torch.Tensor, List]]:
+        if not isinstance(camera, Cameras):
+            print("Called get_outputs with not a camera")
+            return {}
+        assert camera.shape[0] == 1, "Only one camera at a time"
+        if self.training:
+            bc = getattr(self.config, "background_color", "random")
+            if bc == "random":
+                background = torch.rand(3, device=self.device)
+            elif bc == "white":
+                background = torch.ones(3, device=self.device)
+            elif bc == "black":
+                background = torch.zeros(3, device=self.device)
+            else:
+                background = self.background_color.to(self.device)
+        else:
+            background = self.background_color.to(self.device)
+        params = {k: getattr(self, k) for k in ("means", "scales", "quats", "features_dc", "features_rest", "opacities")}
+        if self.crop_box is not None and not self.training:
+            crop_ids = self.crop_box.within(self.means).squeeze()
+            if crop_ids.sum() == 0:
+                return {"rgb": background.repeat(int(camera.height.item()), int(camera.width.item()), 1)}
+            params = {k: v[crop_ids] for k, v in params.items()}
+        W, H = int(camera.width.item()), int(camera.height.item())
+        self.last_size = (H, W)
+        sh_degree = getattr(self.config, "sh_degree", 3)
+        n = min(self.step // getattr(self.config, "sh_degree_interval", 1000), sh_degree) if sh_degree > 0 else -1
+        state: dict = {}
+        out = render_gaussians(params, camera.camera_to_worlds[0], camera.fx.item(), camera.fy.item(), camera.cx.item(),
+                               camera.cy.item(), H, W, n, background, training=self.training, state=state)
+        self.xys, self.radii = state.get("xys"), state.get("radii")
+        return out
+
+    @torch.no_grad()
+    def get_outputs_for_camera(self, camera: Cameras, obb_box=None) -> Dict[str, torch.Tensor]:
+        assert camera is not None, "must provide camera to gaussian model"
+        self.set_crop(obb_box)
+        self.training = False
+        outs = self.get_outputs(camera.to(self.device))
+        self.training = True
+        return outs  # type: ignore

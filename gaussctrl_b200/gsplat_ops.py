@@ -1,0 +1,133 @@
+"""The gsplat operator seam on the sm_100a rasteriser kernels.
+
+Same call signatures as gsplat 0.1.3's `project_gaussians`, `spherical_harmonics`, `rasterize_gaussians` as the
+reference calls them (gaussctrl/gc_model.py:140-154, :166, :174-186, :191-202), plus `rasterize_rgbd`, the fused
+rgb+depth+alpha pass `GaussCtrlModel.get_outputs` uses here instead of two rasterize calls."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import check, lib
+
+BLOCK = 16
+_p = ops._p
+_stream = ops._stream
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("gaussctrl_b200 rasteriser needs CUDA tensors (there is no CPU path)")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _host16(m: torch.Tensor):
+    m = m.detach().to("cpu", torch.float32)
+    if m.shape[0] == 3:
+        m = torch.cat([m, torch.tensor([[0.0, 0.0, 0.0, 1.0]])], dim=0)
+    return (ctypes.c_float * 16)(*m.reshape(-1).tolist())
+
+
+def project_gaussians(means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, img_height, img_width,
+                      tile_bounds, clip_thresh: float = 0.01):
+    """-> (xys [N,2], depths [N], radii [N] i32, conics [N,3], num_tiles_hit [N] i32, cov3d [N,6])."""
+    means3d, scales, quats = _f32(means3d), _f32(scales), _f32(quats)
+    N, dev = means3d.shape[0], means3d.device
+    xys = torch.empty((N, 2), dtype=torch.float32, device=dev)
+    depths = torch.empty((N,), dtype=torch.float32, device=dev)
+    radii = torch.empty((N,), dtype=torch.int32, device=dev)
+    conics = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    nth = torch.empty((N,), dtype=torch.int32, device=dev)
+    cov3d = torch.empty((N, 6), dtype=torch.float32, device=dev)
+    check(lib.gcb_project_gaussians_fwd(_p(means3d), _p(scales), float(glob_scale), _p(quats), _host16(viewmat),
+                                        _host16(projmat), float(fx), float(fy), float(cx), float(cy), int(img_height),
+                                        int(img_width), int(tile_bounds[0]), int(tile_bounds[1]), float(clip_thresh), N,
+                                        _p(xys), _p(depths), _p(radii), _p(conics), _p(nth), _p(cov3d), _stream()))
+    ops.LAUNCHES[0] += 1
+    return xys, depths, radii, conics, nth, cov3d
+
+
+def spherical_harmonics(degrees_to_use: int, viewdirs, coeffs):
+    viewdirs, coeffs = _f32(viewdirs), _f32(coeffs)
+    N, K = coeffs.shape[0], coeffs.shape[1]
+    colors = torch.empty((N, 3), dtype=torch.float32, device=coeffs.device)
+    check(lib.gcb_sh_fwd(int(degrees_to_use), K, _p(viewdirs), _p(coeffs), _p(colors), N, _stream()))
+    ops.LAUNCHES[0] += 1
+    return colors
+
+
+def bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds, want_keys: bool = False):
+    """Depth-order the Gaussians, emit tile intersections, group by tile.
+    -> (gaussian_ids [M] i32, tile_bins [T,2] i32, isect_keys [M] i64 or None, M)."""
+    N, dev = depths.shape[0], depths.device
+    tbx, tby = int(tile_bounds[0]), int(tile_bounds[1])
+    sorted_ids = torch.empty((N,), dtype=torch.int32, device=dev)
+    cum = torch.empty((N,), dtype=torch.int32, device=dev)
+    nb = lib.gcb_depth_order_workspace_bytes(N)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    check(lib.gcb_depth_order(_p(depths), _p(num_tiles_hit), N, _p(sorted_ids), _p(cum), _p(ws), nb, _stream()))
+    ops.LAUNCHES[0] += 16
+    M = int(cum[-1].item())  # the one host sync gsplat's rasterize_gaussians also has
+    gids = torch.empty((max(M, 1),), dtype=torch.int32, device=dev)
+    bins = torch.empty((tbx * tby, 2), dtype=torch.int32, device=dev)
+    keys = torch.empty((max(M, 1),), dtype=torch.int64, device=dev) if want_keys else None
+    nb2 = lib.gcb_bin_tiles_workspace_bytes(N, M, tbx, tby)
+    ws2 = torch.empty(max(nb2, 16), dtype=torch.uint8, device=dev)
+    check(lib.gcb_bin_tiles(_p(xys), _p(depths), _p(radii), _p(sorted_ids), _p(cum), N, M, tbx, tby, _p(gids), _p(bins),
+                            _p(keys), _p(ws2), ws2.numel(), _stream()))
+    ops.LAUNCHES[0] += 6
+    return gids[:M], bins, (keys[:M] if keys is not None else None), M
+
+
+def rasterize_sorted(xys, conics, colors, opacity, gids, bins, img_height, img_width, background):
+    """-> (img [H,W,C], final_T [H,W], final_idx [H,W])"""
+    colors = _f32(colors)
+    C = colors.shape[1]
+    dev = colors.device
+    H, W = int(img_height), int(img_width)
+    out = torch.empty((H, W, C), dtype=torch.float32, device=dev)
+    fT = torch.empty((H, W), dtype=torch.float32, device=dev)
+    fidx = torch.empty((H, W), dtype=torch.int32, device=dev)
+    bg = (ctypes.c_float * C)(*[float(v) for v in background.detach().cpu().reshape(-1).tolist()])
+    check(lib.gcb_rasterize_fwd(_p(_f32(xys)), _p(_f32(conics)), _p(colors), _p(_f32(opacity).reshape(-1)), _p(gids),
+                                _p(bins), H, W, C, bg, _p(out), _p(fT), _p(fidx), _stream()))
+    ops.LAUNCHES[0] += 1
+    return out, fT, fidx
+
+
+def rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width,
+                        background: Optional[torch.Tensor] = None, return_alpha: bool = False):
+    """gsplat 0.1.3 signature (forward).  colors [N,C], C in {1,3,4}."""
+    C = colors.shape[-1]
+    dev = colors.device
+    if background is None:
+        background = torch.ones(C, dtype=torch.float32, device=dev)
+    tile_bounds = ((img_width + BLOCK - 1) // BLOCK, (img_height + BLOCK - 1) // BLOCK, 1)
+    gids, bins, _, M = bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds)
+    if M < 1:
+        img = torch.ones(img_height, img_width, C, device=dev) * background.to(dev)
+        return (img, torch.zeros(img_height, img_width, device=dev)) if return_alpha else img
+    img, fT, _ = rasterize_sorted(xys, conics, colors, opacity, gids, bins, img_height, img_width, background)
+    return (img, 1.0 - fT) if return_alpha else img
+
+
+def rasterize_rgbd(xys, depths, radii, conics, num_tiles_hit, rgbs, opacity, img_height, img_width, background):
+    """Fused replacement of the reference's two rasterize calls + epilogue (gc_model.py:174-204):
+    one binning, one 4-channel composite (r,g,b,depth), then rgb=min(rgb,1), depth=depth/alpha (1000 where alpha==0).
+    -> (rgb [H,W,3], depth [H,W,1], alpha [H,W,1])"""
+    dev = rgbs.device
+    H, W = int(img_height), int(img_width)
+    tile_bounds = ((W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK, 1)
+    gids, bins, _, M = bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds)
+    col4 = torch.cat([_f32(rgbs), _f32(depths)[:, None]], dim=1).contiguous()
+    bg4 = torch.cat([background.detach().to(dev, torch.float32).reshape(3), torch.zeros(1, device=dev)])
+    img4, fT, _ = rasterize_sorted(xys, conics, col4, opacity, gids, bins, H, W, bg4)
+    rgb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((H, W, 1), dtype=torch.float32, device=dev)
+    alpha = torch.empty((H, W, 1), dtype=torch.float32, device=dev)
+    check(lib.gcb_raster_finalize(_p(img4), _p(fT), _p(rgb), _p(depth), _p(alpha), H * W, _stream()))
+    ops.LAUNCHES[0] += 1
+    return rgb, depth, alpha

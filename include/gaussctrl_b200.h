@@ -78,8 +78,10 @@ int gcb_geglu_pack_rows(int Cout, int32_t* h_perm);
 /* GroupNorm (+ optional SiLU) over channels-last input, optionally over the channel-concatenation of two
  * tensors (UNet skip connections): y[B,HW,C1+C2] = act(GN(cat(x1, x2))).  fp32 statistics.
  * Replaces: torch.nn.GroupNorm + F.silu in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out. */
+size_t gcb_groupnorm_workspace_bytes(int B, int groups);
 int gcb_groupnorm_nhwc_fwd(const void* x1, const void* x2, const void* gamma, const void* beta, void* y, int B, int HW,
-                           int C1, int C2, int groups, float eps, int silu, void* stream);
+                           int C1, int C2, int groups, float eps, int silu, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 /* LayerNorm over the last dim: y[M,C]. Replaces torch.nn.LayerNorm in BasicTransformerBlock. */
 int gcb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int M, int C, float eps,
@@ -93,9 +95,13 @@ int gcb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* 
  * The reference's 5 passes are n_src=5, weights {c, (1-c)/4 x4}, src rows {b, ref0..ref3 of b's CFG half}
  * (utils.py:88-117); text cross-attention and the vanilla AttnProcessor are n_src=1.
  * ld_* are row strides in elements (>= heads*d) so q/k/v may be slices of a fused QKV projection. */
+#define GCB_ATTN_AUTO 0     /* tcgen05 kernel where it is built for the shape, else the mma.sync kernel */
+#define GCB_ATTN_TCGEN05 1
+#define GCB_ATTN_MMA_SYNC 2
 int gcb_attn_multi_fwd(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2,
                        const void* v2, int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d,
-                       int n_src, const int32_t* src_index, const float* h_src_weight, float scale, void* stream);
+                       int n_src, const int32_t* src_index, const float* h_src_weight, float scale, int impl,
+                       void* stream);
 
 /* Row softmax with scale, fp16 in/out, fp32 math (VAE mid-block attention, 1 head of dim 512). */
 int gcb_softmax_rows_fwd(const void* x, void* y, int rows, int cols, float scale, void* stream);
@@ -105,17 +111,19 @@ int gcb_silu_fwd(const void* x, void* y, long long n, void* stream);
 int gcb_add_fwd(const void* a, const void* b, void* y, long long n, float alpha, float beta, void* stream);
 int gcb_geglu_fwd(const void* x, void* y, int M, int C, void* stream); /* x [M,2C] -> y [M,C] = x[:, :C]*gelu(x[:, C:]) */
 int gcb_upsample_nearest2x_nhwc(const void* x, void* y, int B, int H, int W, int C, void* stream);
-int gcb_timestep_embedding(const float* h_timesteps, int B, int dim, void* y /* fp16 [B,dim] */, void* stream);
+/* timesteps: DEVICE float[B] (so one captured CUDA graph serves every DDIM step) */
+int gcb_timestep_embedding(const float* timesteps, int B, int dim, void* y /* fp16 [B,dim] */, void* stream);
 int gcb_nchw_to_nhwc_f16(const void* x, void* y, int B, int C, int H, int W, void* stream);
 int gcb_nhwc_to_nchw_f16(const void* x, void* y, int B, int C, int H, int W, void* stream);
-int gcb_transpose_f16(const void* x, void* y, int rows, int cols, void* stream);
+int gcb_transpose_f16(const void* x, void* y, int batch, int rows, int cols, void* stream);
 
 /* Classifier-free-guidance combine + DDIM step (eta = 0), replaces
  * `noise_pred_uncond + g*(noise_pred_text - noise_pred_uncond)` and `DDIMScheduler.step` inside pipe() (:209-219);
  * with eps_cond == NULL it is the plain (inverse) DDIM update used by DDIMInverseScheduler (:141-145).
- *   x' = sqrt(a_prev) * (x - sqrt(1-a_t) * eps) / sqrt(a_t) + sqrt(1-a_prev) * eps       (fp32 math, fp16 storage) */
+ *   x' = sqrt(a_prev) * (x - sqrt(1-a_t) * eps) / sqrt(a_t) + sqrt(1-a_prev) * eps       (fp32 math, fp16 storage)
+ * coef: DEVICE float[4] = {sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)} (graph-replayable per step). */
 int gcb_cfg_ddim_step(const void* eps_uncond, const void* eps_cond, const void* x, void* x_out, long long n,
-                      float guidance, float alpha_t, float alpha_prev, void* stream);
+                      float guidance, const float* coef, void* stream);
 
 /* (x/2+0.5).clamp(0,1) on the decoded image + optional mask composite edited*m + unedited*(1-m)
  * (gc_pipeline.py:223-234); img [B,H,W,3] fp16 NHWC -> out [B,H,W,3] fp32. mask [B,H,W] fp32 or NULL. */
@@ -143,30 +151,25 @@ int gcb_project_gaussians_fwd(const float* means3d, const float* scales, float g
 
 /* gsplat.spherical_harmonics forward: viewdirs [N,3] (unit), coeffs [N,K,3], colors [N,3]. */
 int gcb_sh_fwd(int degree, int K, const float* viewdirs, const float* coeffs, float* colors, int N, void* stream);
-/* backward: v_coeffs [N,K,3] (written, zero beyond the active degree) */
-int gcb_sh_bwd(int degree, int K, const float* viewdirs, const float* v_colors, float* v_coeffs, int N, void* stream);
-
-/* Fused B200 path of GaussCtrlModel.get_outputs (gc_model.py:138-167): exp(scales), quat normalisation,
- * projection, view direction, SH colour (+0.5, clamp >= 0) and sigmoid(opacity) in ONE pass over the
- * 236 B/Gaussian parameter record.  Outputs as gcb_project_gaussians_fwd plus rgbs [N,3], opac [N]. */
-int gcb_project_sh_fused_fwd(const float* means3d, const float* log_scales, const float* quats,
-                             const float* features_dc, const float* features_rest, const float* opacity_logits,
-                             const float* h_viewmat, const float* h_projmat, const float* h_cam_origin, float fx,
-                             float fy, float cx, float cy, int img_h, int img_w, int tile_bx, int tile_by,
-                             int sh_degree, int N, float* xys, float* depths, int32_t* radii, float* conics,
-                             int32_t* num_tiles_hit, float* rgbs, float* opac, void* stream);
-
-/* Inclusive prefix sum of num_tiles_hit -> cum_tiles_hit (int32 [N]); workspace via gcb_scan_workspace_bytes. */
+/* Inclusive prefix sum (torch.cumsum inside gsplat.rasterize_gaussians); workspace via gcb_scan_workspace_bytes. */
 size_t gcb_scan_workspace_bytes(int N);
 int gcb_cumsum_i32(const int32_t* in, int32_t* out, int N, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Tile binning: map_gaussian_to_intersects + stable radix sort by (tile_id << 32 | depth bits) + tile bin edges.
- * M = cum_tiles_hit[N-1] (the caller reads it back, as gsplat does). Outputs: isect_keys [M] i64 (sorted),
- * gaussian_ids [M] i32 (sorted), tile_bins [tile_bx*tile_by, 2] i32. */
-size_t gcb_bin_sort_workspace_bytes(int N, long long M);
-int gcb_bin_and_sort(const float* xys, const float* depths, const int32_t* radii, const int32_t* cum_tiles_hit, int N,
-                     long long M, int tile_bx, int tile_by, int64_t* isect_keys, int32_t* gaussian_ids,
-                     int32_t* tile_bins, void* workspace, size_t workspace_bytes, void* stream);
+/* Tile binning (gsplat map_gaussian_to_intersects + torch.sort + get_tile_bin_edges, inside each
+ * rasterize_gaussians call, gc_model.py:174-186 and :191-202), re-designed: order the N Gaussians by depth
+ * once (stable, ties by id), emit their tile intersections in that order, one stable radix pass by tile id.
+ * The result equals a STABLE sort of (tile_id << 32 | depth bits) keys.
+ *   step 1  gcb_depth_order: sorted_ids [N] and cum_sorted [N] = inclusive cumsum of num_tiles_hit in that order;
+ *           the caller reads M = cum_sorted[N-1] back (the one host sync gsplat also has).
+ *   step 2  gcb_bin_tiles:   gaussian_ids [M] (sorted), tile_bins [tiles,2] (start,end; 0,0 for empty tiles),
+ *           optional isect_keys [M] i64 (NULL to skip; needs depths). */
+size_t gcb_depth_order_workspace_bytes(int N);
+int gcb_depth_order(const float* depths, const int32_t* num_tiles_hit, int N, int32_t* sorted_ids, int32_t* cum_sorted,
+                    void* workspace, size_t workspace_bytes, void* stream);
+size_t gcb_bin_tiles_workspace_bytes(int N, long long M, int tile_bx, int tile_by);
+int gcb_bin_tiles(const float* xys, const float* depths, const int32_t* radii, const int32_t* sorted_ids,
+                  const int32_t* cum_sorted, int N, long long M, int tile_bx, int tile_by, int32_t* gaussian_ids,
+                  int32_t* tile_bins, int64_t* isect_keys, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-tile front-to-back alpha compositing (gsplat rasterize_forward).  colors [N,C] with C in {1,3,4};
  * background host float[C].  Outputs: out_img [H,W,C], final_T [H,W], final_idx [H,W] i32.
@@ -175,21 +178,6 @@ int gcb_bin_and_sort(const float* xys, const float* depths, const int32_t* radii
 int gcb_rasterize_fwd(const float* xys, const float* conics, const float* colors, const float* opacities,
                       const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
                       const float* h_background, float* out_img, float* final_T, int32_t* final_idx, void* stream);
-
-/* gsplat rasterize_backward: v_out [H,W,C] (and optional v_out_alpha [H,W]) -> v_xy [N,2], v_conic [N,3],
- * v_colors [N,C], v_opacity [N] (all must be zero-initialised by the caller; accumulated with atomics). */
-int gcb_rasterize_bwd(const float* xys, const float* conics, const float* colors, const float* opacities,
-                      const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
-                      const float* h_background, const float* final_T, const int32_t* final_idx, const float* v_out,
-                      const float* v_out_alpha, float* v_xy, float* v_conic, float* v_colors, float* v_opacity,
-                      void* stream);
-
-/* gsplat project_gaussians backward: (v_xy, v_depth, v_conic) -> v_means3d [N,3], v_scales [N,3], v_quats [N,4]. */
-int gcb_project_gaussians_bwd(const float* means3d, const float* scales, float glob_scale, const float* quats,
-                              const float* h_viewmat, const float* h_projmat, float fx, float fy, float cx, float cy,
-                              int img_h, int img_w, const int32_t* radii, const float* conics, const float* v_xy,
-                              const float* v_depth, const float* v_conic, int N, float* v_means3d, float* v_scales,
-                              float* v_quats, void* stream);
 
 /* get_outputs epilogue (gc_model.py:188,203-204): rgb = min(rgb,1); depth = depth/alpha where alpha>0 else 1000.
  * in: img4 [H,W,4] (r,g,b,depth-accum), final_T [H,W]; out: rgb [H,W,3], depth [H,W,1], alpha [H,W,1]. */

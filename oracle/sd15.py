@@ -277,7 +277,7 @@ class UNet2DConditionModel(nn.Module):
 
     def forward(self, sample, t, ehs, down_res: Optional[Sequence[torch.Tensor]] = None, mid_res=None):
         tt = torch.as_tensor(t).reshape(-1).expand(sample.shape[0])
-        temb = self.time_embedding(timestep_embedding(tt, self.ch[0]).to(sample.dtype))
+        temb = self.time_embedding(timestep_embedding(tt.cpu(), self.ch[0]).to(device=sample.device, dtype=sample.dtype))
         x = self.conv_in(sample)
         skips = [x]
         for blk in self.down_blocks:
@@ -341,7 +341,7 @@ class ControlNetModel(nn.Module):
 
     def forward(self, sample, t, ehs, cond, conditioning_scale: float = 1.0):
         tt = torch.as_tensor(t).reshape(-1).expand(sample.shape[0])
-        temb = self.time_embedding(timestep_embedding(tt, self.ch[0]).to(sample.dtype))
+        temb = self.time_embedding(timestep_embedding(tt.cpu(), self.ch[0]).to(device=sample.device, dtype=sample.dtype))
         x = self.conv_in(sample) + self.controlnet_cond_embedding(cond)
         skips = [x]
         for blk in self.down_blocks:

@@ -1,0 +1,142 @@
+"""GPU parity of the ControlNet+UNet denoiser and of the two DDIM loops against the oracle (oracle/sd15.py,
+oracle/pipeline.py) with the same seeded full-width SD1.x weights.  The oracle runs in fp32 (on the GPU, TF32 off, so
+the test finishes in seconds); the product computes in fp16 with fp32 accumulation.  Tolerance: the fp16 band the
+reference itself lives in - rel-RMS 2e-2 on eps after ~60 layers, stated per check."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HW = 32  # 32x32 latents (256x256 conditioning image): same architecture, 4x fewer tokens than 512^2
+
+
+@pytest.fixture(scope="module")
+def models():
+    from oracle import sd15
+    from gaussctrl_b200.diffusion import SD15Denoiser
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    unet, cnet, _ = sd15.seeded_models(seed=0, with_vae=False)
+    den = SD15Denoiser(unet.state_dict(), cnet.state_dict(), "cuda")
+    unet, cnet = unet.cuda(), cnet.cuda()
+    return unet, cnet, den
+
+
+def _inputs(F, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn((F, 4, HW, HW), generator=g)
+    disp = torch.rand((F, 1, HW * 8, HW * 8), generator=g).repeat(1, 3, 1, 1)
+    pos = torch.randn((1, 77, 768), generator=g)
+    neg = torch.randn((1, 77, 768), generator=g)
+    # the product stores latents / conditioning / embeddings in fp16: give the oracle the same rounded values
+    r = lambda t: t.half().float()  # noqa: E731
+    return r(lat), r(disp), r(pos), r(neg)
+
+
+def _rel(got, want):
+    got, want = got.float().cpu(), want.float().cpu()
+    return ((got - want).norm() / want.norm()).item()
+
+
+def test_eps_crossview_matches_oracle(models):
+    from oracle import sd15
+    from gaussctrl_b200 import ops
+    from gaussctrl_b200.diffusion import literal_crossview_plan
+    unet, cnet, den = models
+    F = 5
+    lat, disp, pos, neg = _inputs(F)
+    t = 501
+    with torch.no_grad():
+        unet.set_attn_processor(sd15.CrossViewProcessor(0.6, 2))
+        cnet.set_attn_processor(sd15.CrossViewProcessor(0.0, 2))
+        ehs = torch.cat([neg.expand(F, -1, -1), pos.expand(F, -1, -1)]).cuda()
+        xin = torch.cat([lat, lat]).cuda()
+        cond = torch.cat([disp, disp]).cuda()
+        down, mid = cnet(xin, t, ehs, cond, 1.0)
+        want = unet(xin, t, ehs, down, mid)
+    den.set_prompts(torch.cat([neg, pos]))
+    x = ops.nchw_to_nhwc(xin.half())
+    cemb = den.controlnet_cond(ops.nchw_to_nhwc(cond.half()))
+    # conditioning embedding alone first (fp16 direct convs)
+    with torch.no_grad():
+        want_c = cnet.controlnet_cond_embedding(cond)
+    assert _rel(ops.nhwc_to_nchw(cemb), want_c) < 5e-3
+    tdev = torch.full((2 * F,), float(t), device="cuda")
+    got = ops.nhwc_to_nchw(den.eps(x, tdev, cemb, literal_crossview_plan(F, "cuda")))
+    torch.cuda.synchronize()
+    rel = _rel(got, want)
+    assert rel < 2e-2, rel
+
+
+def test_eps_vanilla_matches_oracle(models):
+    from oracle import sd15
+    from gaussctrl_b200 import ops
+    from gaussctrl_b200.diffusion import vanilla_plan
+    unet, cnet, den = models
+    lat, disp, pos, _ = _inputs(2, seed=1)
+    t = 51
+    with torch.no_grad():
+        unet.set_attn_processor(sd15.vanilla_processor)
+        cnet.set_attn_processor(sd15.vanilla_processor)
+        ehs = pos.expand(2, -1, -1).cuda()
+        down, mid = cnet(lat.cuda(), t, ehs, disp.cuda(), 1.0)
+        want = unet(lat.cuda(), t, ehs, down, mid)
+    den.set_prompts(pos)
+    cemb = den.controlnet_cond(ops.nchw_to_nhwc(disp.cuda().half()))
+    got = den.eps(ops.nchw_to_nhwc(lat.cuda().half()), torch.full((2,), float(t), device="cuda"), cemb,
+                  vanilla_plan(2, "cuda"))
+    rel = _rel(ops.nhwc_to_nchw(got), want)
+    assert rel < 2e-2, rel
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_edit_loop_matches_oracle(models, use_graphs):
+    """S=3 steps of the reference-schedule edit loop (refs + chunk, CFG) vs oracle.pipeline.edit_chunk."""
+    from oracle import pipeline as opipe, sd15
+    from gaussctrl_b200.engine import EditEngine
+    unet, cnet, den = models
+    R, c, S, g = 4, 2, 3, 5.0
+    lat, disp, pos, neg = _inputs(R + c, seed=2)
+    want = opipe.edit_chunk(unet, cnet, None, sd15.DDIMTables(), lat.cuda(), disp.cuda(), pos.cuda(), neg.cuda(), S, g, R,
+                            decode=False)
+    eng = EditEngine(den, use_graphs=use_graphs)
+    got = eng.edit_reference_schedule(lat, disp, pos, neg, S, g, R)
+    torch.cuda.synchronize()
+    rel = _rel(got, want)
+    assert rel < 2e-2, rel  # fp16 latents after 3 steps vs fp32 oracle
+
+
+def test_refs_once_schedule_equals_reference_schedule(models):
+    """The B200 schedule (references denoised once, K/V recorded, views batched independently) gives the same latents
+    as the reference's per-chunk schedule - reference rows never depend on chunk rows."""
+    from gaussctrl_b200.engine import EditEngine
+    unet, cnet, den = models
+    V, R, c, S, g = 7, 4, 3, 2, 5.0
+    lat, disp, pos, neg = _inputs(V, seed=3)
+    ref_idx = [1, 2, 4, 6]
+    eng = EditEngine(den, use_graphs=True)
+    got = eng.edit_refs_once(lat, disp, ref_idx, pos, neg, S, g, view_batch=2)
+    non_ref = [v for v in range(V) if v not in ref_idx]
+    sel = ref_idx + non_ref
+    want = eng.edit_reference_schedule(lat[sel], disp[sel], pos, neg, S, g, R)  # chunk rows = non-ref views
+    rel = _rel(got[non_ref], want)
+    assert rel < 1e-3, rel
+    # a reference view edited as an ordinary chunk view equals its row of the reference pass (gotcha 6)
+    sel2 = ref_idx + [ref_idx[0]]
+    want2 = eng.edit_reference_schedule(lat[sel2], disp[sel2], pos, neg, S, g, R)
+    assert _rel(got[ref_idx[0]:ref_idx[0] + 1], want2) < 1e-3
+
+
+def test_inversion_matches_oracle(models):
+    from oracle import pipeline as opipe, sd15
+    from gaussctrl_b200.engine import EditEngine
+    unet, cnet, den = models
+    S = 3
+    lat, disp, pos, _ = _inputs(3, seed=4)
+    eng = EditEngine(den, use_graphs=True)
+    got = eng.invert(lat * 0.5, disp, pos, S, batch=2)
+    for v in range(3):
+        want = opipe.invert_view(unet, cnet, sd15.DDIMTables(), (lat[v:v + 1] * 0.5).cuda(), disp[v:v + 1].cuda(),
+                                 pos.cuda(), S)
+        rel = _rel(got[v:v + 1], want)
+        assert rel < 2e-2, rel

@@ -1,0 +1,9 @@
+#!/bin/bash
+# One GPU visit: kernel parity tests per file (isolated processes, bounded by timeout), logs into gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+for f in "$@"; do
+  name=$(basename $f .py)
+  timeout 900 python -m pytest $f -q -m gpu -p no:cacheprovider --timeout 300 2>&1 | tail -n 80 > gpurun_out/$name.log
+  echo "== $name: exit ${PIPESTATUS[0]}"; tail -n 25 gpurun_out/$name.log
+done
