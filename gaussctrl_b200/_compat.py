@@ -19,11 +19,15 @@ except Exception:  # ModuleNotFoundError here
 
     class Cameras:  # the attributes GaussCtrlModel.get_outputs reads (gc_model.py:65-113)
         def __init__(self, camera_to_worlds, fx, fy, cx, cy, width, height):
-            t = lambda v: torch.as_tensor(v, dtype=torch.float32).reshape(-1, 1)  # noqa: E731
             self.camera_to_worlds = torch.as_tensor(camera_to_worlds, dtype=torch.float32).reshape(-1, 3, 4)
+            n = self.camera_to_worlds.shape[0]
+
+            def t(v, dtype=torch.float32):  # scalars broadcast over the n cameras, like nerfstudio's Cameras
+                v = torch.as_tensor(v, dtype=dtype).reshape(-1, 1)
+                return v.expand(n, 1).contiguous() if v.shape[0] == 1 and n > 1 else v
+
             self.fx, self.fy, self.cx, self.cy = t(fx), t(fy), t(cx), t(cy)
-            self.width = torch.as_tensor(width).reshape(-1, 1)
-            self.height = torch.as_tensor(height).reshape(-1, 1)
+            self.width, self.height = t(width, torch.int64), t(height, torch.int64)
 
         @property
         def shape(self):

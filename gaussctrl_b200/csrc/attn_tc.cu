@@ -1,14 +1,398 @@
-// tcgen05 multi-source attention (placeholder until the TMEM kernel lands: reports "unsupported" for every shape so
-// GCB_ATTN_AUTO resolves to the mma.sync kernel).
+// Multi-source (cross-view) attention on the 5th-gen tensor cores, head dim 40 (the SD1.x 64x64 level: 75 % of the
+// attention FLOPs of the hot path).
+//
+//   out[b, i, h, :] = sum_s w_s * softmax_j( q[b,i,h,:] . K_s[j,h,:] * scale ) V_s[j,h,:]      (utils.py:25-37, 88-117)
+//
+// One CTA = 256 query rows (two 128-row slots A/B) of one (batch row, head).  Warp roles (320 threads):
+//   warps 0-3 / 4-7 : softmax of slot A / B - one query row per thread, S read from TMEM (tcgen05.ld), exp2 on packed
+//                     halves (ex2.approx.f16x2), P written to shared memory in the 128B-swizzled K-major layout
+//   warp 8          : TMA producer (Q once; K and V tiles of 128 keys through 3-stage mbarrier rings)
+//   warp 9          : TMEM allocator + single-thread tcgen05.mma issuer:
+//                       S   = Q K^T          M128 x N128 x K48  (Q/K tiles are 64-column TMA boxes; columns 40..47 of Q
+//                                                                are zeroed in smem so the neighbouring head's columns
+//                                                                that ride along in K contribute nothing)
+//                       O  += P V            M128 x N48  x K128 (V used MN-major straight from its row-major tile)
+//                       l  += P 1            M128 x N16  x K128 (row sums on the tensor core, fp32 in TMEM)
+// Online softmax with lazy rescaling: the running max only moves when a tile exceeds it by 2^8, so the O/l
+// correction (TMEM load-scale-store) is rare.  Sources are processed back to back; at the end of each source the slot
+// folds O * w_s / l into fp32 registers.  TMEM: S_A[0,128) S_B[128,256) O_A[256,304) l_A[304,320) O_B[320,368)
+// l_B[368,384).
 #include "../../include/gaussctrl_b200.h"
 #include "common.cuh"
 
-int gcb_attn_tc_supported(int Nq, int Nk, int heads, int d) {
-    (void)Nq; (void)Nk; (void)heads; (void)d;
-    return 0;
+namespace {
+
+constexpr int MAX_SRC = 8;
+constexpr int D = 40;
+constexpr int BM = 128;           // query rows per slot
+constexpr int BN = 128;           // keys per tile
+constexpr int KSTAGES = 3, VSTAGES = 3;
+constexpr uint32_t TILE_BYTES = 128 * 128;  // one 128-row x 64-halves TMA box
+constexpr uint32_t TM_S_A = 0, TM_S_B = 128, TM_O_A = 256, TM_L_A = 304, TM_O_B = 320, TM_L_B = 368;
+constexpr float RESCALE_THRESHOLD = 8.f;
+
+struct AttnTcParams {
+    __half* out;
+    int ld_out;
+    int Nq, Nk, heads;
+    int q_col0, k_col0, v_col0, k2_col0, v2_col0;  // column of head 0 inside each tensor map
+    int n_src_total, n_act;
+    int src_id[MAX_SRC];
+    float weight[MAX_SRC];
+    const int32_t* src_index;
+    float scale_log2;
+};
+
+struct __align__(1024) Smem {
+    uint8_t q[2][TILE_BYTES];
+    uint8_t k[KSTAGES][TILE_BYTES];
+    uint8_t v[VSTAGES][TILE_BYTES];
+    uint8_t p[2][2][TILE_BYTES];   // [slot][64-key half]
+    uint8_t ones[2048];            // 16 rows x 128 B of fp16 1.0 (B operand of the row-sum MMA; any layout: all ones)
+    uint64_t q_full, q_ready;
+    uint64_t k_full[KSTAGES], k_empty[KSTAGES], v_full[VSTAGES], v_empty[VSTAGES];
+    uint64_t s_full[2], s_free[2], p_ready[2], p_free[2], o_free[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) { mbar_arrive(bar); }
+
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
 }
-int gcb_attn_tc_launch(const void*, int, const void*, const void*, int, const void*, const void*, int, void*, int, int,
-                       int, int, int, int, int, const int32_t*, const float*, float, cudaStream_t) {
-    gcb_set_error("tcgen05 attention kernel not built");
-    return GCB_ERR_UNSUPPORTED;
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+    uint32_t y;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
+    return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(320, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
+               const __grid_constant__ CUtensorMap tmV2, const AttnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int nkt = p.Nk / BN;
+    const int T = p.n_act * nkt;  // (source, key tile) pairs, processed in order
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&sm.q_full), 1);
+        mbar_init(smem_u32(&sm.q_ready), 256);
+        for (int i = 0; i < KSTAGES; ++i) {
+            mbar_init(smem_u32(&sm.k_full[i]), 1);
+            mbar_init(smem_u32(&sm.k_empty[i]), 1);
+        }
+        for (int i = 0; i < VSTAGES; ++i) {
+            mbar_init(smem_u32(&sm.v_full[i]), 1);
+            mbar_init(smem_u32(&sm.v_empty[i]), 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(smem_u32(&sm.s_full[t]), 1);
+            mbar_init(smem_u32(&sm.s_free[t]), 128);
+            mbar_init(smem_u32(&sm.p_ready[t]), 128);
+            mbar_init(smem_u32(&sm.p_free[t]), 1);
+            mbar_init(smem_u32(&sm.o_free[t]), 128);
+        }
+        mbar_fence_init();
+    }
+    // fp16 ones for the row-sum MMA
+    for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm.ones)[i] = 0x3C003C00u;
+    if (warp == 9) {
+        tmem_alloc(smem_u32(&sm.tmem_base), 512);
+        tmem_relinquish();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp == 8) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            const uint32_t qf = smem_u32(&sm.q_full);
+            mbar_expect_tx(qf, 2 * TILE_BYTES);
+            const int qrow = b * p.Nq + qt * 2 * BM;
+            tma_load_2d(smem_u32(sm.q[0]), &tmQ, qf, p.q_col0 + head * D, qrow);
+            tma_load_2d(smem_u32(sm.q[1]), &tmQ, qf, p.q_col0 + head * D, qrow + BM);
+            for (int i = 0; i < T; ++i) {
+                const int s = i / nkt, j = i - s * nkt;
+                const int sidx = p.src_index[b * p.n_src_total + p.src_id[s]];
+                const bool second = sidx < 0;
+                const int row = (second ? -(sidx + 1) : sidx) * p.Nk + j * BN;
+                {
+                    const int st = i % KSTAGES;
+                    mbar_wait(smem_u32(&sm.k_empty[st]), (((uint32_t)(i / KSTAGES)) & 1u) ^ 1u);
+                    const uint32_t fb = smem_u32(&sm.k_full[st]);
+                    mbar_expect_tx(fb, TILE_BYTES);
+                    tma_load_2d(smem_u32(sm.k[st]), second ? &tmK2 : &tmK, fb, (second ? p.k2_col0 : p.k_col0) + head * D,
+                                row);
+                }
+                {
+                    const int st = i % VSTAGES;
+                    mbar_wait(smem_u32(&sm.v_empty[st]), (((uint32_t)(i / VSTAGES)) & 1u) ^ 1u);
+                    const uint32_t fb = smem_u32(&sm.v_full[st]);
+                    mbar_expect_tx(fb, TILE_BYTES);
+                    tma_load_2d(smem_u32(sm.v[st]), second ? &tmV2 : &tmV, fb, (second ? p.v2_col0 : p.v_col0) + head * D,
+                                row);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
+            const uint32_t idesc_pv = make_idesc_f16(BM, 48, 0, 1);   // B = V, MN-major
+            const uint32_t idesc_l = make_idesc_f16(BM, 16, 0, 0);
+            const uint64_t ones_desc = make_smem_desc(smem_u32(sm.ones), 16, 1024, 2);
+            mbar_wait(smem_u32(&sm.q_ready), 0);
+            tc_fence_after();
+            auto issue_qk = [&](int t, int i) {
+                const int st = i % KSTAGES;
+                if (t == 0) {
+                    mbar_wait(smem_u32(&sm.k_full[st]), ((uint32_t)(i / KSTAGES)) & 1u);
+                }
+                if (i > 0) mbar_wait(smem_u32(&sm.s_free[t]), ((uint32_t)(i - 1)) & 1u);
+                tc_fence_after();
+                const uint64_t qd = make_smem_desc(smem_u32(sm.q[t]), 16, 1024, 2);
+                const uint64_t kd = make_smem_desc(smem_u32(sm.k[st]), 16, 1024, 2);
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks)
+                    tc_mma_ss(tmem + (t ? TM_S_B : TM_S_A), qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_qk,
+                              (uint32_t)(ks != 0));
+                tc_commit(smem_u32(&sm.s_full[t]));
+                if (t == 1) tc_commit(smem_u32(&sm.k_empty[st]));
+            };
+            auto issue_pv = [&](int t, int i) {
+                const int s = i / nkt, j = i - s * nkt;
+                const int st = i % VSTAGES;
+                if (t == 0) mbar_wait(smem_u32(&sm.v_full[st]), ((uint32_t)(i / VSTAGES)) & 1u);
+                mbar_wait(smem_u32(&sm.p_ready[t]), ((uint32_t)i) & 1u);
+                if (j == 0 && s > 0) mbar_wait(smem_u32(&sm.o_free[t]), ((uint32_t)(s - 1)) & 1u);
+                tc_fence_after();
+                const uint32_t o_t = tmem + (t ? TM_O_B : TM_O_A), l_t = tmem + (t ? TM_L_B : TM_L_A);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    // A: P [128 x 16 keys] of 64-key half kk/4, 32 B further per k-step; B: V rows (keys) 16*kk.., 128 B each
+                    const uint64_t pd = make_smem_desc(smem_u32(sm.p[t][kk >> 2]) + (uint32_t)((kk & 3) * 32), 16, 1024, 2);
+                    const uint64_t vd = make_smem_desc(smem_u32(sm.v[st]) + (uint32_t)(kk * 2048), 1024, 1024, 2);
+                    const uint32_t acc = (uint32_t)((j | kk) != 0);
+                    tc_mma_ss(o_t, pd, vd, idesc_pv, acc);
+                    tc_mma_ss(l_t, pd, ones_desc, idesc_l, acc);
+                }
+                tc_commit(smem_u32(&sm.p_free[t]));
+                if (t == 1) tc_commit(smem_u32(&sm.v_empty[st]));
+            };
+            issue_qk(0, 0);
+            issue_qk(1, 0);
+            for (int i = 0; i < T; ++i) {
+                if (i + 1 < T) issue_qk(0, i + 1);
+                issue_pv(0, i);
+                if (i + 1 < T) issue_qk(1, i + 1);
+                issue_pv(1, i);
+            }
+        }
+    } else {
+        // ===================================================================== softmax slots
+        const int t = warp >> 2;            // slot
+        const int wq = warp & 3;            // TMEM lane quarter
+        const int row = wq * 32 + lane;     // row inside the slot
+        const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
+        const uint32_t s_t = tmem + lane_base + (t ? TM_S_B : TM_S_A);
+        const uint32_t o_t = tmem + lane_base + (t ? TM_O_B : TM_O_A);  // O[0,48) then l[48,64)
+        // zero Q columns 40..47 (16-byte chunk 5 of the 128B-swizzled row), then publish Q to the MMA thread
+        mbar_wait(smem_u32(&sm.q_full), 0);
+        {
+            uint8_t* qrow = sm.q[t] + (row >> 3) * 1024 + (row & 7) * 128 + ((5 ^ (row & 7)) * 16);
+            *reinterpret_cast<uint4*>(qrow) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&sm.q_ready));
+
+        float oacc[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) oacc[c] = 0.f;
+        uint8_t* prow = sm.p[t][0] + (row >> 3) * 1024 + (row & 7) * 128;
+        const int sw = row & 7;
+
+        for (int s = 0; s < p.n_act; ++s) {
+            float m = -INFINITY;  // running reference max, exp2 domain
+            for (int j = 0; j < nkt; ++j) {
+                const int i = s * nkt + j;
+                mbar_wait(smem_u32(&sm.s_full[t]), ((uint32_t)i) & 1u);
+                tc_fence_after();
+                uint32_t sr[128];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t tmp[32];
+                    tmem_ld_32x32b_x32(s_t + (uint32_t)(c * 32), tmp);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) sr[c * 32 + e] = tmp[e];
+                }
+                tc_wait_ld();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&sm.s_free[t]));
+                // tile max (raw scores; scale > 0 so max commutes with scaling)
+                float mx = __uint_as_float(sr[0]);
+#pragma unroll
+                for (int e = 1; e + 1 < 128; e += 2) mx = fmax3(mx, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
+                mx = fmaxf(mx, __uint_as_float(sr[127])) * p.scale_log2;
+                // P(i-1) must have been consumed (and O(i-1) accumulated) before P is overwritten / O rescaled
+                if (i > 0) {
+                    mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
+                    tc_fence_after();
+                }
+                if (j == 0) {
+                    m = mx;
+                } else {
+                    const bool grow = mx > m + RESCALE_THRESHOLD;
+                    if (__any_sync(0xffffffffu, grow)) {
+                        const float alpha = grow ? exp2f(m - mx) : 1.f;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t ov[16];
+                            tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                            tmem_st_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                        }
+                        tc_wait_st();
+                        if (grow) m = mx;
+                    }
+                }
+                // p = 2^(s*scale - m) on packed halves, written as the K-major SW128 A operand of P V
+                const float negm = -m;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float x0 = fmaf(__uint_as_float(sr[c * 8 + 2 * e]), p.scale_log2, negm);
+                        const float x1 = fmaf(__uint_as_float(sr[c * 8 + 2 * e + 1]), p.scale_log2, negm);
+                        w[e] = ex2_f16x2(cvt_f16x2(x0, x1));
+                    }
+                    uint8_t* dst = prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) * 16);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&sm.p_ready[t]));
+            }
+            // ---- end of source: out += w_s * O / l
+            const int ilast = s * nkt + nkt - 1;
+            mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)ilast) & 1u);
+            tc_fence_after();
+            uint32_t ov[32], ov2[16], lv[16];
+            tmem_ld_32x32b_x32(o_t, ov);
+            tmem_ld_32x32b_x16(o_t + 32, ov2);
+            tmem_ld_32x32b_x16(o_t + 48, lv);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sm.o_free[t]));
+            const float wl = p.weight[s] / __uint_as_float(lv[0]);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) oacc[c] += __uint_as_float(ov[c]) * wl;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) oacc[32 + c] += __uint_as_float(ov2[c]) * wl;
+        }
+        // ---- store the row: 40 halves = 5 x 16 B
+        const long long grow_ = (long long)b * p.Nq + qt * 2 * BM + t * BM + row;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + grow_ * p.ld_out + head * D);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            uint4 o;
+            o.x = pack_half2(oacc[c * 8 + 0], oacc[c * 8 + 1]);
+            o.y = pack_half2(oacc[c * 8 + 2], oacc[c * 8 + 3]);
+            o.z = pack_half2(oacc[c * 8 + 4], oacc[c * 8 + 5]);
+            o.w = pack_half2(oacc[c * 8 + 6], oacc[c * 8 + 7]);
+            dst[c] = o;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+int encode_rows(CUtensorMap* tm, const void* base, int ld, long long rows, int width) {
+    const uint64_t dims[2] = {(uint64_t)width, (uint64_t)rows};
+    const uint64_t strides[1] = {(uint64_t)ld * 2};
+    const uint32_t box[2] = {64, 128};
+    return gcb_encode_tma(tm, base, 2, dims, strides, box, 1);
+}
+
+}  // namespace
+
+int gcb_attn_tc_supported(int Nq, int Nk, int heads, int d) {
+    (void)heads;
+    return d == D && Nq % (2 * BM) == 0 && Nk % BN == 0 && Nk >= BN;
+}
+
+int gcb_attn_tc_launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2, const void* v2,
+                       int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d, int n_src,
+                       const int32_t* src_index, const float* h_src_weight, float scale, cudaStream_t stream) {
+    (void)d;
+    AttnTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = (__half*)out;
+    p.ld_out = ld_out;
+    p.Nq = Nq;
+    p.Nk = Nk;
+    p.heads = heads;
+    p.n_src_total = n_src;
+    for (int s = 0; s < n_src; ++s)
+        if (h_src_weight[s] != 0.f) {
+            p.src_id[p.n_act] = s;
+            p.weight[p.n_act] = h_src_weight[s];
+            ++p.n_act;
+        }
+    if (p.n_act == 0) {
+        gcb_set_error("all source weights are zero");
+        return GCB_ERR_INVALID;
+    }
+    p.src_index = src_index;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    GCB_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
+                      ((uintptr_t)out % 16) == 0 && ld_out % 8 == 0,
+                  "tcgen05 attention needs 16-byte aligned q/k/v/out");
+    // tensor maps: inner extent = heads*d columns from each base pointer (columns beyond are zero-filled by TMA, so the
+    // 64-wide box of the last head never reads past its tensor).  The batch-row count of the K/V buffers is not part
+    // of the ABI: rows are addressed through src_index, extent is left open.
+    const int width = heads * D;
+    const long long big = 1ll << 31;
+    CUtensorMap tmQ, tmK, tmV, tmK2, tmV2;
+    int rc;
+    if ((rc = encode_rows(&tmQ, q, ld_q, (long long)B * Nq, width))) return rc;
+    if ((rc = encode_rows(&tmK, k, ld_kv, big, width))) return rc;
+    if ((rc = encode_rows(&tmV, v, ld_kv, big, width))) return rc;
+    if (k2) {
+        if ((rc = encode_rows(&tmK2, k2, ld_kv2, big, width))) return rc;
+        if ((rc = encode_rows(&tmV2, v2, ld_kv2, big, width))) return rc;
+    } else {
+        tmK2 = tmK;
+        tmV2 = tmV;
+    }
+    const size_t smem = sizeof(Smem) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        GCB_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(Nq / (2 * BM), heads, B);
+    attn_tc_kernel<<<grid, 320, smem, stream>>>(tmQ, tmK, tmV, tmK2, tmV2, p);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
 }

@@ -355,8 +355,8 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     static size_t configured_smem = 0;
     if (smem > configured_smem) {
-        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured_smem = 227 * 1024;
+        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        configured_smem = 225 * 1024;
     }
     dim3 grid(gcb_cdiv(Cout, p.BN), gcb_cdiv(M, BM));
     gemm_tc_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, p);

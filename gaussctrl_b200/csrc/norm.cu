@@ -9,25 +9,23 @@
 namespace {
 
 constexpr int GN_MAX_GROUPS = 32;
-constexpr int GN_MAX_CHUNKS = 64;
+constexpr int GN_MAX_CHUNKS = 256;
 
 __device__ __forceinline__ const __half* gn_src(const __half* x1, const __half* x2, int C1, int C2, long long pix,
                                                 int c) {
     return c < C1 ? x1 + pix * C1 + c : x2 + pix * C2 + (c - C1);
 }
 
-// partial[b][chunk][g][2] = (sum, sumsq) over the chunk's pixels
+// partial[b][chunk][g][2] = (sum, sumsq) over the chunk's pixels.  Deterministic: every thread owns fixed
+// (row-group, column-pair) cells and the per-group reduction walks them in a fixed order (no atomics).
+constexpr int GN_MAX_CELLS = 1280 + 256;  // column pairs (C <= 2560) or 256 threads' cells for narrow tensors
+
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2,
                                                        float* __restrict__ partial, int HW, int C1, int C2, int groups,
                                                        int pix_per_chunk) {
-    __shared__ float s_sum[GN_MAX_GROUPS], s_sq[GN_MAX_GROUPS];
+    __shared__ float s_sum[GN_MAX_CELLS], s_sq[GN_MAX_CELLS];
     const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const int C = C1 + C2, cols = C / 2, cpg = C / groups;
-    if (tid < groups) {
-        s_sum[tid] = 0.f;
-        s_sq[tid] = 0.f;
-    }
-    __syncthreads();
     const int p0 = chunk * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
     const int rgroups = cols >= 256 ? 1 : 256 / cols;
     const int rg = cols >= 256 ? 0 : tid / cols;
@@ -41,16 +39,23 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
                 sum += f.x + f.y;
                 sq += f.x * f.x + f.y * f.y;
             }
-            atomicAdd(&s_sum[c / cpg], sum);
-            atomicAdd(&s_sq[c / cpg], sq);
+            s_sum[rg * cols + col] = sum;
+            s_sq[rg * cols + col] = sq;
             if (cols < 256) break;
         }
     }
     __syncthreads();
     if (tid < groups) {
+        const int c0 = tid * cpg / 2, c1 = (tid + 1) * cpg / 2;  // cpg is even: groups own whole column pairs
+        float sum = 0.f, sq = 0.f;
+        for (int r = 0; r < rgroups; ++r)
+            for (int col = c0; col < c1; ++col) {
+                sum += s_sum[r * cols + col];
+                sq += s_sq[r * cols + col];
+            }
         float* o = partial + (((long long)b * gridDim.x + chunk) * groups + tid) * 2;
-        o[0] = s_sum[tid];
-        o[1] = s_sq[tid];
+        o[0] = sum;
+        o[1] = sq;
     }
 }
 
@@ -183,7 +188,7 @@ extern "C" int gcb_groupnorm_nhwc_fwd(const void* x1, const void* x2, const void
     GCB_CHECK_ARG(x1 && gamma && beta && y && workspace, "null pointer");
     GCB_CHECK_ARG(C2 == 0 || x2, "x2 is NULL but C2=%d", C2);
     GCB_CHECK_ARG(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0, "bad groups=%d for C=%d", groups, C);
-    GCB_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C / groups) % 2 == 0, "channel counts C1=%d C2=%d unsupported", C1, C2);
+    GCB_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0 && (C / groups) % 2 == 0 && C <= 2560, "channel counts C1=%d C2=%d unsupported", C1, C2);
     if (workspace_bytes < gcb_groupnorm_workspace_bytes(B, groups)) {
         gcb_set_error("groupnorm workspace too small");
         return GCB_ERR_WORKSPACE;

@@ -157,7 +157,7 @@ class SD15Denoiser:
         self.fuse_geglu = fuse_geglu
         self.ch = [unet_sd[f"down_blocks.{i}.resnets.0.conv1.weight"].shape[0] for i in range(4)]
         self._temb_layout: Dict[int, Tuple[List[str], Dict[str, int], int]] = {}
-        self.text_kv: Dict[Tuple[int, str], torch.Tensor] = {}
+        self.text_kv: Dict[Tuple[int, str, int], torch.Tensor] = {}
 
     # ---------------------------------------------------------------------------------------- per-run constants
     def set_prompts(self, embeds: torch.Tensor) -> None:
@@ -165,11 +165,16 @@ class SD15Denoiser:
         embeds = embeds.to(device=self.dev, dtype=torch.float16).contiguous()
         self.n_prompts = embeds.shape[0]
         self.text_len = embeds.shape[1]
-        self.text_kv.clear()
         for net_id, net in ((0, self.unet), (1, self.cnet)):
             for name in sorted({k[: k.index(".attn2.") + 6] for k in net.sd if ".attn2.to_k.weight" in k}):
                 w, _ = net.cat_lin([name + ".to_k", name + ".to_v"])
-                self.text_kv[(net_id, name)] = ops.linear(embeds, w)  # [P,77,2C]
+                kv = ops.linear(embeds, w)  # [P,77,2C]
+                key = (net_id, name, self.n_prompts)
+                old = self.text_kv.get(key)
+                if old is not None and old.shape == kv.shape:
+                    old.copy_(kv)  # captured CUDA graphs hold the address of this buffer
+                else:
+                    self.text_kv[key] = kv
 
     def controlnet_cond(self, cond_nhwc: torch.Tensor) -> torch.Tensor:
         """controlnet_cond_embedding (3->16->16->32->32->96->96->256->C0 convs with SiLU): [B,512,512,3] -> [B,64,64,C0].
@@ -249,7 +254,7 @@ class SD15Denoiser:
         n2 = ops.layernorm(h, net.vec(blk + ".norm2.weight"), net.vec(blk + ".norm2.bias"))
         wq, _ = net.lin(blk + ".attn2.to_q")
         q = ops.linear(n2, wq)
-        tkv = self.text_kv[(net_id, blk + ".attn2")]
+        tkv = self.text_kv[(net_id, blk + ".attn2", self.n_prompts)]
         a = ops.attention(q, 0, C, tkv, 0, C, 2 * C, None, 0, 0, 0, B, N, self.text_len, heads, d, plan.text_index, [1.0])
         wo, bo = net.lin(blk + ".attn2.to_out.0")
         h = ops.linear(a, wo, bo, residual=h)

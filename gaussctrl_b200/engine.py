@@ -82,6 +82,7 @@ class EditEngine:
         self.dev = denoiser.dev
         self.tables = tables or DDIMTables()
         self.use_graphs = use_graphs
+        self._steps: Dict[tuple, object] = {}  # captured graphs are reused across calls (static buffers inside)
 
     # ------------------------------------------------------------------------------------------ helpers
     def _latents_in(self, z_nchw: torch.Tensor) -> torch.Tensor:
@@ -107,13 +108,13 @@ class EditEngine:
         cond = self._cond_emb(disparity)
         x_all = self._latents_in(z0)
         out = torch.empty_like(x_all)
-        steps: Dict[int, _GraphedStep] = {}
         ts = self.tables.inverse_timesteps(S)
         for i in range(0, V, batch):
             n = min(batch, V - i)
-            if n not in steps:
-                steps[n] = _GraphedStep(self.den, n, False, 0.0, vanilla_plan(n, self.dev), hw, self.use_graphs)
-            st = steps[n]
+            key = ("invert", n, hw)
+            if key not in self._steps:
+                self._steps[key] = _GraphedStep(self.den, n, False, 0.0, vanilla_plan(n, self.dev), hw, self.use_graphs)
+            st = self._steps[key]
             st.x.copy_(x_all[i:i + n])
             st.set_cond(cond[i:i + n])
             for t in ts:
@@ -132,8 +133,11 @@ class EditEngine:
         assert guidance > 1.0, "the reference assumes CFG doubling (utils.py:94)"
         F, hw = latents.shape[0], latents.shape[-1]
         self.den.set_prompts(torch.cat([neg_embed, pos_embed], dim=0))
-        st = _GraphedStep(self.den, F, True, guidance, literal_crossview_plan(F, self.dev, ref_frames), hw,
-                          self.use_graphs)
+        key = ("reference", F, hw, float(guidance), tuple(ref_frames))
+        if key not in self._steps:
+            self._steps[key] = _GraphedStep(self.den, F, True, guidance, literal_crossview_plan(F, self.dev, ref_frames),
+                                            hw, self.use_graphs)
+        st = self._steps[key]
         st.x.copy_(self._latents_in(latents))
         st.set_cond(self._cond_emb(disparity))
         for t in self.tables.timesteps(S):
@@ -160,15 +164,18 @@ class EditEngine:
         need = sorted(set(non_ref) | set(ref_indices))
         cond_map = {v: c for v, c in zip(need, self._cond_emb(disparity[need]))}
         # (1) reference pass
-        rec: Dict[str, torch.Tensor] = {}
-        ref_step = _GraphedStep(self.den, R, True, guidance,
-                                literal_crossview_plan(R, self.dev, ref_frames, record_kv=rec), hw, self.use_graphs)
+        bsz = min(view_batch, max(1, len(non_ref)))
+        key = ("refs_once", R, bsz, hw, float(guidance), tuple(ref_frames))
+        if key not in self._steps:
+            rec0: Dict[str, torch.Tensor] = {}
+            self._steps[key] = [_GraphedStep(self.den, R, True, guidance,
+                                             literal_crossview_plan(R, self.dev, ref_frames, record_kv=rec0), hw,
+                                             self.use_graphs), rec0, None]
+        ref_step, rec, view_step = self._steps[key]
         ref_step.x.copy_(x_all[list(ref_indices)])
         ref_step.set_cond(torch.stack([cond_map[v] for v in ref_indices]))
         # (2) view batches (the last one is padded by repeating its final view so one graph serves all)
         batches: List[List[int]] = [non_ref[i:i + view_batch] for i in range(0, len(non_ref), view_batch)]
-        bsz = min(view_batch, max(1, len(non_ref)))
-        view_step: Optional[_GraphedStep] = None
         x_views: List[torch.Tensor] = []
         conds: List[torch.Tensor] = []
         for b in batches:
@@ -183,6 +190,7 @@ class EditEngine:
             if batches and view_step is None:
                 view_step = _GraphedStep(self.den, bsz, True, guidance,
                                          cached_crossview_plan(bsz, R, self.dev, rec, ref_frames), hw, self.use_graphs)
+                self._steps[key][2] = view_step
             for bi in range(len(batches)):
                 view_step.x.copy_(x_views[bi])
                 view_step.set_cond(conds[bi])

@@ -1,0 +1,233 @@
+"""GaussCtrlPipeline on the B200 kernels: host-side mirror of gaussctrl/gc_pipeline.py:48-291.
+
+Same config fields and defaults, same constructor signature, same methods (`render_reverse`, `edit_images`,
+`image2latent`, `depth2disparity`, `depth2disparity_torch`, `update_datasets`) and the same `train_data[i]` dict schema
+(`image`, `image_idx`, `unedited_image`, `depth_image`, `z_0_image`, `mask_image`; dtypes/shapes of
+gc_pipeline.py:268-274 and :234), so the reference's trainer (`gc_trainer.py:75-78`) drives it unchanged.
+What changed is below the seam: rasterisation, VAE, ControlNet+UNet, cross-view attention and the DDIM updates are
+the sm_100a kernels of this package, views are batched, and the reference views are denoised once per step instead
+of once per chunk (engine.EditEngine.edit_refs_once)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import random
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Type
+
+import numpy as np
+import torch
+
+from . import ops
+from ._compat import HAVE_NERFSTUDIO, VanillaPipeline, VanillaPipelineConfig
+from .diffusion import SD15Denoiser
+from .engine import EditEngine
+from .sd15_spec import DDIMTables, synthetic_weights
+from .vae import VaeB200
+
+ADDED_PROMPT = "best quality, extremely detailed"
+NEGATIVE_PROMPT = ("longbody, lowres, bad anatomy, bad hands, missing fingers, extra digit, fewer digits, cropped, "
+                   "worst quality, low quality")
+
+
+def select_ref_indices(view_num: int, ref_view_num: int) -> List[int]:
+    """gc_pipeline.py:109-114 with the same seed; `random.randint` is inclusive so the reference can return
+    `view_num` (out of range, SURVEY §8a gotcha 3): clamped to the last view here."""
+    anchors = [(view_num * i) // ref_view_num for i in range(ref_view_num)] + [view_num]
+    random.seed(13789)
+    idx = [random.randint(a, anchors[i + 1]) for i, a in enumerate(anchors[:-1])]
+    return [min(i, view_num - 1) for i in idx]
+
+
+def synthetic_prompt_embeds(prompts: Sequence[str], seq: int = 77, dim: int = 768) -> torch.Tensor:
+    """Stand-in for the CLIP text encoder when no checkpoint is on disk: a deterministic N(0,1) embedding per prompt
+    string.  (CLIP itself is outside the hot path: it runs once per `pipe()` call in the reference.)"""
+    out = []
+    for p in prompts:
+        seed = int.from_bytes(hashlib.sha256(p.encode()).digest()[:8], "little") % (2 ** 63)
+        out.append(torch.randn((seq, dim), generator=torch.Generator().manual_seed(seed)))
+    return torch.stack(out)
+
+
+@dataclass
+class GaussCtrlPipelineConfig(VanillaPipelineConfig):
+    """Field names, types and defaults of gaussctrl/gc_pipeline.py:48-73."""
+    _target: Type = field(default_factory=lambda: GaussCtrlPipeline)
+    datamanager: Any = None
+    render_rate: int = 500
+    edit_prompt: str = ""
+    reverse_prompt: str = ""
+    langsam_obj: str = ""
+    guidance_scale: float = 5
+    num_inference_steps: int = 20
+    chunk_size: int = 5
+    ref_view_num: int = 4
+    diffusion_ckpt: str = "CompVis/stable-diffusion-v1-4"
+    # --- B200 extensions (defaults keep the reference's results)
+    edit_schedule: str = "refs_once"      # or "reference": refs recomputed in every chunk, as gc_pipeline.py:190-219
+    synthetic_seed: int = 0               # weights seed when diffusion_ckpt is not a local checkpoint directory
+
+
+class GaussCtrlPipeline(VanillaPipeline):
+    config: GaussCtrlPipelineConfig
+
+    def __init__(self, config: GaussCtrlPipelineConfig, device: str, test_mode: str = "val", world_size: int = 1,
+                 local_rank: int = 0, grad_scaler: Optional[Any] = None, *, datamanager: Any = None, model: Any = None,
+                 weights: Optional[tuple] = None, prompt_encoder: Optional[Callable] = None,
+                 mask_fn: Optional[Callable] = None):
+        super().__init__(config, device, test_mode, world_size, local_rank)
+        if not HAVE_NERFSTUDIO:
+            self.datamanager = datamanager if datamanager is not None else config.datamanager
+            self._model = model
+        self.config = config
+        self.device_ = torch.device(device)
+        self.test_mode = test_mode
+        self.world_size, self.local_rank = world_size, local_rank
+        self.mask_fn = mask_fn  # LangSAM stays external: any callable rgb[H,W,3] -> mask[H,W]
+        self.edit_prompt = config.edit_prompt
+        self.reverse_prompt = config.reverse_prompt
+        self.pipe_device = self.device_
+        if weights is None:
+            weights = self._load_weights(config.diffusion_ckpt, config.synthetic_seed)
+        unet_sd, cnet_sd, vae_sd = weights
+        self.denoiser = SD15Denoiser(unet_sd, cnet_sd, self.device_)
+        self.vae = VaeB200(vae_sd, self.device_) if vae_sd is not None else None
+        self.tables = DDIMTables()
+        self.engine = EditEngine(self.denoiser, self.tables)
+        self.prompt_encoder = prompt_encoder or synthetic_prompt_embeds
+        self.positive_prompt = self.edit_prompt + ", " + ADDED_PROMPT
+        self.positive_reverse_prompt = self.reverse_prompt + ", " + ADDED_PROMPT
+        self.negative_prompts = NEGATIVE_PROMPT
+        view_num = len(self.datamanager.cameras)
+        self.ref_indices = select_ref_indices(view_num, config.ref_view_num)
+        self.num_ref_views = len(self.ref_indices)
+        self.num_inference_steps = config.num_inference_steps
+        self.guidance_scale = config.guidance_scale
+        self.controlnet_conditioning_scale = 1.0
+        self.eta = 0.0
+        self.chunk_size = config.chunk_size
+
+    @staticmethod
+    def _load_weights(ckpt: str, seed: int):
+        if os.path.isdir(ckpt):
+            raise NotImplementedError("loading safetensors checkpoints: key names already match sd15_spec; wire "
+                                      "safetensors.torch.load_file here when a checkpoint is on disk")
+        return synthetic_weights(seed)
+
+    # ------------------------------------------------------------------------------------------ stage A
+    @torch.no_grad()
+    def render_reverse(self):
+        """Render rgb + depth of every view, encode, and DDIM-invert to z_T (gc_pipeline.py:122-157).
+        The reference loops views at batch 1; here the three stages each run over all views in batches."""
+        cams = self.datamanager.cameras
+        V = len(cams)
+        rgbs, depths = [], []
+        for cam_idx in range(V):
+            out = self._model.get_outputs_for_camera(cams[cam_idx].to(self.device_))
+            rgbs.append(out["rgb"].to(torch.float16))          # [H,W,3] 0..1   (:132)
+            depths.append(out["depth"].to(torch.float16))      # [H,W,1]        (:133)
+        rgb = torch.stack(rgbs)
+        depth = torch.stack(depths)
+        z0 = torch.cat([self.image2latent_batch(rgb[i:i + 4]) for i in range(0, V, 4)])
+        disparity = ops.depth_to_disparity(depth[..., 0].float().contiguous(), True)   # depth2disparity_torch on fp16
+        disparity = ops.nhwc_to_nchw(disparity)
+        emb = self.prompt_encoder([self.positive_reverse_prompt])
+        zT = self.engine.invert(z0, disparity, emb, self.num_inference_steps)
+        for cam_idx in range(V):
+            mask = None
+            if self.config.langsam_obj != "" and self.mask_fn is not None:
+                mask = np.asarray(self.mask_fn(rgb[cam_idx].cpu(), self.config.langsam_obj)) * 1
+            self.update_datasets(cam_idx, rgb[cam_idx].cpu(), depth[cam_idx], zT[cam_idx:cam_idx + 1], mask)
+
+    # ------------------------------------------------------------------------------------------ stage B
+    @torch.no_grad()
+    def edit_images(self):
+        """Edit every view with ControlNet + cross-view attention and write the result into
+        `train_data[i]["image"]` as [H,W,3] fp32 on the CPU (gc_pipeline.py:159-237)."""
+        td = self.datamanager.train_data
+        V = len(td)
+        dev = self.device_
+        z = torch.from_numpy(np.concatenate([d["z_0_image"] for d in td], axis=0)).pin_memory()
+        dep = torch.from_numpy(np.concatenate([d["depth_image"] for d in td], axis=0)).pin_memory()
+        z_dev = z.to(dev, non_blocking=True).to(torch.float16)
+        dep_dev = dep.to(dev, non_blocking=True)
+        self.h2d_bytes = z.numel() * 4 + dep.numel() * 4
+        # depth2disparity (numpy fp32, then .to(float16): gc_pipeline.py:182-186, 198-200), per view
+        disparity = ops.nhwc_to_nchw(ops.depth_to_disparity(dep_dev.contiguous(), False))
+        emb = self.prompt_encoder([self.negative_prompts, self.positive_prompt])
+        neg, pos = emb[0:1], emb[1:2]
+        S, g = self.num_inference_steps, float(self.guidance_scale)
+        if self.config.edit_schedule == "reference":
+            R = self.num_ref_views
+            outs = []
+            for i in range(0, V, self.chunk_size):
+                sel = list(self.ref_indices) + list(range(i, min(V, i + self.chunk_size)))
+                outs.append(self.engine.edit_reference_schedule(z_dev[sel], disparity[sel], pos, neg, S, g, R))
+            lat = torch.cat(outs)
+        else:
+            lat = self.engine.edit_refs_once(z_dev, disparity, self.ref_indices, pos, neg, S, g,
+                                             view_batch=max(1, self.chunk_size))
+        masks = uned = None
+        if all("mask_image" in d for d in td):
+            masks = torch.from_numpy(np.stack([np.asarray(d["mask_image"], dtype=np.float32) for d in td])).to(dev)
+            uned = torch.stack([d["unedited_image"] for d in td]).to(dev, torch.float16)
+            self.h2d_bytes += masks.numel() * 4 + uned.numel() * 2
+        imgs = self.vae.decode_latents(lat, masks, uned)               # [V,H,W,3] fp32
+        host = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(imgs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes = host.numel() * 4
+        for i in range(V):
+            td[int(td[i].get("image_idx", i))]["image"] = host[i]   # global_idx = image_idx (gc_pipeline.py:224,234)
+
+    # ------------------------------------------------------------------------------------------ helpers (same names)
+    @torch.no_grad()
+    def image2latent(self, image: torch.Tensor) -> torch.Tensor:
+        """[H,W,3] in 0..1 -> [1,4,h,w] (gc_pipeline.py:239-246)."""
+        return self.image2latent_batch(image[None])
+
+    @torch.no_grad()
+    def image2latent_batch(self, images: torch.Tensor) -> torch.Tensor:
+        return self.vae.encode_mean(images.to(self.device_))
+
+    def depth2disparity(self, depth):
+        """numpy [1,H,W] -> [1,3,H,W] (gc_pipeline.py:248-256)."""
+        d = torch.from_numpy(np.ascontiguousarray(depth, dtype=np.float32)).to(self.device_)
+        out = ops.nhwc_to_nchw(ops.depth_to_disparity(d, False))
+        return out.float().cpu().numpy()
+
+    def depth2disparity_torch(self, depth: torch.Tensor) -> torch.Tensor:
+        """torch [1,H,W] -> [1,3,H,W] (gc_pipeline.py:258-266), fp16 arithmetic when the input is fp16."""
+        d = depth.to(self.device_)
+        out = ops.nhwc_to_nchw(ops.depth_to_disparity(d.float().contiguous(), d.dtype == torch.float16))
+        return out.to(depth.dtype)
+
+    def update_datasets(self, cam_idx, unedited_image, depth, latent, mask):
+        """gc_pipeline.py:268-274."""
+        td = self.datamanager.train_data[cam_idx]
+        td["unedited_image"] = unedited_image
+        td["depth_image"] = depth.permute(2, 0, 1).cpu().to(torch.float32).numpy()
+        td["z_0_image"] = latent.cpu().to(torch.float32).numpy()
+        if mask is not None:
+            td["mask_image"] = mask
+
+    def get_train_loss_dict(self, step: int):
+        ray_bundle, batch = self.datamanager.next_train(step)
+        model_outputs = self._model(ray_bundle)
+        metrics_dict = self.model.get_metrics_dict(model_outputs, batch)
+        loss_dict = self.model.get_loss_dict(model_outputs, batch, metrics_dict)
+        return model_outputs, loss_dict, metrics_dict
+
+    def forward(self):
+        raise NotImplementedError
+
+
+class SimpleDataManager:
+    """Minimal datamanager carrying what the hot path touches: `cameras` and the `train_data` list of dicts
+    (the full GaussCtrlDataManager - image loading, undistortion, view sub-sampling, gc_datamanager.py - is I/O
+    outside the hot path)."""
+
+    def __init__(self, cameras, train_data: Optional[List[Dict]] = None):
+        self.cameras = cameras
+        n = len(cameras)
+        self.train_data = train_data if train_data is not None else [{"image_idx": i} for i in range(n)]

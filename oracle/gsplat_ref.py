@@ -69,10 +69,17 @@ def viewmat_from_c2w(c2w: torch.Tensor) -> torch.Tensor:
     return vm
 
 
+def _sqrt(x: torch.Tensor) -> torch.Tensor:
+    """Correctly rounded fp32 square root.  torch.sqrt on CPU goes through MKL VML and is NOT correctly rounded
+    (0.6 % of inputs are 1 ulp off); sqrt in fp64 followed by rounding to fp32 is (53 >= 2*24+2 bits), which is what
+    IEEE hardware sqrt (CUDA __fsqrt_rn, numpy) returns."""
+    return torch.sqrt(x.double()).to(x.dtype)
+
+
 def _quat_to_rotmat(q: torch.Tensor):
     """gsplat quat_to_rotmat: (w,x,y,z), normalised inside."""
     w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-    inv = 1.0 / torch.sqrt(((w * w + x * x) + y * y) + z * z)
+    inv = 1.0 / _sqrt(((w * w + x * x) + y * y) + z * z)
     w, x, y, z = w * inv, x * inv, y * inv, z * inv
     r00 = 1.0 - 2.0 * (y * y + z * z)
     r01 = 2.0 * (x * y - w * z)
@@ -120,8 +127,9 @@ def project_gaussians(means3d, scales, glob_scale, quats, viewmat, projmat, fx, 
 
     # EWA projection
     fx32, fy32 = np.float32(fx), np.float32(fy)
-    tan_fovx = np.float32(0.5 * img_width / fx)
-    tan_fovy = np.float32(0.5 * img_height / fy)
+    # gsplat's kernel receives fx, fy as fp32 and evaluates `0.5 * img_size / fx` in double (0.5 is a double literal)
+    tan_fovx = np.float32(0.5 * img_width / float(fx32))
+    tan_fovy = np.float32(0.5 * img_height / float(fy32))
     lim_x = float(np.float32(1.3) * tan_fovx)
     lim_y = float(np.float32(1.3) * tan_fovy)
     tz_safe = torch.where(valid, tz, torch.ones_like(tz))
@@ -157,10 +165,10 @@ def project_gaussians(means3d, scales, glob_scale, quats, viewmat, projmat, fx, 
     inv_det = 1.0 / det_safe
     conic = torch.stack([c * inv_det, (-b) * inv_det, a * inv_det], dim=-1)
     b_mid = 0.5 * (a + c)
-    disc = torch.sqrt(torch.clamp(b_mid * b_mid - det, min=0.1))
+    disc = _sqrt(torch.clamp(b_mid * b_mid - det, min=0.1))
     v1 = b_mid + disc
     v2 = b_mid - disc
-    radius = torch.ceil(3.0 * torch.sqrt(torch.maximum(v1, v2)))
+    radius = torch.ceil(3.0 * _sqrt(torch.maximum(v1, v2)))
 
     def hom(r):
         return ((pm[r, 0] * px + pm[r, 1] * py) + pm[r, 2] * pz) + pm[r, 3]
