@@ -16,7 +16,7 @@
 // Online softmax with lazy rescaling: the running max only moves when a tile exceeds it by 2^8, so the O/l
 // correction (TMEM load-scale-store) is rare.  Sources are processed back to back; at the end of each source the slot
 // folds O * w_s / l into fp32 registers.  TMEM: S_A[0,128) S_B[128,256) O_A[256,304) l_A[304,320) O_B[320,368)
-// l_B[368,384).
+// l_B[368,384) acc_A[384,432) acc_B[432,480).
 #include "../../include/gaussctrl_b200.h"
 #include "common.cuh"
 
@@ -29,6 +29,7 @@ constexpr int BN = 128;           // keys per tile
 constexpr int KSTAGES = 3, VSTAGES = 3;
 constexpr uint32_t TILE_BYTES = 128 * 128;  // one 128-row x 64-halves TMA box
 constexpr uint32_t TM_S_A = 0, TM_S_B = 128, TM_O_A = 256, TM_L_A = 304, TM_O_B = 320, TM_L_B = 368;
+constexpr uint32_t TM_ACC_A = 384, TM_ACC_B = 432;  // fp32 running sum over sources (48 columns per slot)
 constexpr float RESCALE_THRESHOLD = 8.f;
 
 struct AttnTcParams {
@@ -67,6 +68,22 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
     uint32_t y;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
     return y;
+}
+// tcgen05.ld 32x32b.x32 straight into r[OFF .. OFF+31] (no staging copy)
+template <int OFF>
+__device__ __forceinline__ void tmem_ld32_into(uint32_t taddr, uint32_t (&r)[128]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]),
+          "=r"(r[OFF + 6]), "=r"(r[OFF + 7]), "=r"(r[OFF + 8]), "=r"(r[OFF + 9]), "=r"(r[OFF + 10]), "=r"(r[OFF + 11]),
+          "=r"(r[OFF + 12]), "=r"(r[OFF + 13]), "=r"(r[OFF + 14]), "=r"(r[OFF + 15]), "=r"(r[OFF + 16]),
+          "=r"(r[OFF + 17]), "=r"(r[OFF + 18]), "=r"(r[OFF + 19]), "=r"(r[OFF + 20]), "=r"(r[OFF + 21]),
+          "=r"(r[OFF + 22]), "=r"(r[OFF + 23]), "=r"(r[OFF + 24]), "=r"(r[OFF + 25]), "=r"(r[OFF + 26]),
+          "=r"(r[OFF + 27]), "=r"(r[OFF + 28]), "=r"(r[OFF + 29]), "=r"(r[OFF + 30]), "=r"(r[OFF + 31])
+        : "r"(taddr)
+        : "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
@@ -222,9 +239,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         fence_proxy_async();
         mbar_arrive(smem_u32(&sm.q_ready));
 
-        float oacc[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) oacc[c] = 0.f;
+        const uint32_t acc_t = tmem + lane_base + (t ? TM_ACC_B : TM_ACC_A);
         uint8_t* prow = sm.p[t][0] + (row >> 3) * 1024 + (row & 7) * 128;
         const int sw = row & 7;
 
@@ -235,31 +250,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 mbar_wait(smem_u32(&sm.s_full[t]), ((uint32_t)i) & 1u);
                 tc_fence_after();
                 uint32_t sr[128];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t tmp[32];
-                    tmem_ld_32x32b_x32(s_t + (uint32_t)(c * 32), tmp);
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) sr[c * 32 + e] = tmp[e];
-                }
+                tmem_ld32_into<0>(s_t, sr);
+                tmem_ld32_into<32>(s_t + 32, sr);
+                tmem_ld32_into<64>(s_t + 64, sr);
+                tmem_ld32_into<96>(s_t + 96, sr);
                 tc_wait_ld();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sm.s_free[t]));
-                // tile max (raw scores; scale > 0 so max commutes with scaling)
-                float mx = __uint_as_float(sr[0]);
+                // tile max (raw scores; scale > 0 so max commutes with scaling): four independent chains
+                float mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
+                      mxd = __uint_as_float(sr[3]);
 #pragma unroll
-                for (int e = 1; e + 1 < 128; e += 2) mx = fmax3(mx, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
-                mx = fmaxf(mx, __uint_as_float(sr[127])) * p.scale_log2;
-                // P(i-1) must have been consumed (and O(i-1) accumulated) before P is overwritten / O rescaled
-                if (i > 0) {
-                    mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
-                    tc_fence_after();
+                for (int e = 4; e < 128; e += 8) {
+                    mxa = fmax3(mxa, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
+                    mxb = fmax3(mxb, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
+                    if (e + 4 < 128) {
+                        mxc = fmax3(mxc, __uint_as_float(sr[e + 4]), __uint_as_float(sr[e + 5]));
+                        mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
+                    }
                 }
+                const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)) * p.scale_log2;
+                bool waited = (i == 0);
                 if (j == 0) {
                     m = mx;
                 } else {
                     const bool grow = mx > m + RESCALE_THRESHOLD;
                     if (__any_sync(0xffffffffu, grow)) {
+                        // rare: O(i-1) must be complete before it is rescaled
+                        mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
+                        tc_fence_after();
+                        waited = true;
                         const float alpha = grow ? exp2f(m - mx) : 1.f;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
@@ -274,19 +294,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         if (grow) m = mx;
                     }
                 }
-                // p = 2^(s*scale - m) on packed halves, written as the K-major SW128 A operand of P V
+                // p = 2^(s*scale - m) on packed halves, kept in registers (reusing the score registers) ...
                 const float negm = -m;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    uint32_t w[4];
+                for (int e = 0; e < 64; ++e) {
+                    const float x0 = fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm);
+                    const float x1 = fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm);
+                    sr[e] = ex2_f16x2(cvt_f16x2(x0, x1));
+                }
+                // ... so that the wait for P(i-1) to be consumed by its P V product overlaps the exponentials
+                if (!waited) {
+                    mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
+                    tc_fence_after();
+                }
+                // K-major SW128 A operand of P V: 16-byte chunk c of the row goes to chunk (c ^ row%8) of its 64-key half
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float x0 = fmaf(__uint_as_float(sr[c * 8 + 2 * e]), p.scale_log2, negm);
-                        const float x1 = fmaf(__uint_as_float(sr[c * 8 + 2 * e + 1]), p.scale_log2, negm);
-                        w[e] = ex2_f16x2(cvt_f16x2(x0, x1));
-                    }
+                for (int c = 0; c < 16; ++c) {
                     uint8_t* dst = prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) * 16);
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(sr[c * 4], sr[c * 4 + 1], sr[c * 4 + 2], sr[c * 4 + 3]);
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -296,20 +321,39 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int ilast = s * nkt + nkt - 1;
             mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)ilast) & 1u);
             tc_fence_after();
-            uint32_t ov[32], ov2[16], lv[16];
-            tmem_ld_32x32b_x32(o_t, ov);
-            tmem_ld_32x32b_x16(o_t + 32, ov2);
+            uint32_t lv[16];
             tmem_ld_32x32b_x16(o_t + 48, lv);
             tc_wait_ld();
-            tc_fence_before();
-            mbar_arrive(smem_u32(&sm.o_free[t]));
             const float wl = p.weight[s] / __uint_as_float(lv[0]);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) oacc[c] += __uint_as_float(ov[c]) * wl;
+            for (int c = 0; c < 3; ++c) {   // 48 columns in 3 chunks of 16 (columns 40..47 are don't-care)
+                uint32_t ov[16], av[16];
+                tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                if (s > 0) tmem_ld_32x32b_x16(acc_t + (uint32_t)(c * 16), av);
+                tc_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 8; ++c) oacc[32 + c] += __uint_as_float(ov2[c]) * wl;
+                for (int e = 0; e < 16; ++e) {
+                    const float prev = s > 0 ? __uint_as_float(av[e]) : 0.f;
+                    av[e] = __float_as_uint(fmaf(__uint_as_float(ov[e]), wl, prev));
+                }
+                tmem_st_32x32b_x16(acc_t + (uint32_t)(c * 16), av);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sm.o_free[t]));
         }
         // ---- store the row: 40 halves = 5 x 16 B
+        float oacc[48];
+        {
+            uint32_t a0[32], a1[16];
+            tmem_ld_32x32b_x32(acc_t, a0);
+            tmem_ld_32x32b_x16(acc_t + 32, a1);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) oacc[c] = __uint_as_float(a0[c]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) oacc[32 + c] = __uint_as_float(a1[c]);
+        }
         const long long grow_ = (long long)b * p.Nq + qt * 2 * BM + t * BM + row;
         uint4* dst = reinterpret_cast<uint4*>(p.out + grow_ * p.ld_out + head * D);
 #pragma unroll

@@ -133,8 +133,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         }
     } else {
         // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
-        mbar_wait(smem_u32(&tmem_full_bar), 0);
-        tc_fence_after();
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const long long m = (long long)m_tile * BM + row;
@@ -143,67 +141,105 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int img = (p.rowvec != nullptr && row_ok) ? (int)(m / p.HW) : 0;
         if (p.act != GCB_ACT_GEGLU) {
             const int nchunks = p.BN / 32;
+            const int ncol0 = n_tile * p.BN;
+            const __half* res_row = p.residual ? p.residual + m * p.ldy : nullptr;
+            const __half* rv_row = p.rowvec ? p.rowvec + (long long)img * p.rowvec_ld : nullptr;
+            // software pipeline: the residual of chunk c+1 is in flight while chunk c is converted and stored
+            uint4 res_cur[4], res_nxt[4];
+            auto load_res = [&](int c, uint4 (&dst)[4]) {
+                const int n0 = ncol0 + c * 32;
+                if (res_row && row_ok && n0 + 32 <= p.N) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res_row + n0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) dst[g] = rp[g];
+                }
+            };
+            load_res(0, res_cur);
+            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            tc_fence_after();
             for (int c = 0; c < nchunks; ++c) {
+                const int n0 = ncol0 + c * 32;
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+                if (c + 1 < nchunks) load_res(c + 1, res_nxt);
+                const bool full = n0 + 32 <= p.N;
+                uint4 bv[4], rvv[4];
+                if (full) {
+                    if (p.bias) {
+                        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) bv[g] = bp[g];
+                    }
+                    if (rv_row) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(rv_row + n0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) rvv[g] = rp[g];
+                    }
+                }
                 tc_wait_ld();
-                const int n0 = n_tile * p.BN + c * 32;
-                if (!row_ok || n0 >= p.N) continue;
-                float v[32];
+                if (row_ok && n0 < p.N) {
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                const int nvalid = min(32, p.N - n0);
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) v[j] += __half2float(p.bias[n0 + j]);
-                }
-                if (p.rowvec) {
-                    const __half* rv = p.rowvec + (long long)img * p.rowvec_ld + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) v[j] += __half2float(rv[j]);
-                }
-                if (p.act == GCB_ACT_SILU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-                }
-                __half* yp = p.y + m * p.ldy + n0;
-                if (nvalid == 32) {
-                    if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldy + n0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint4 rr = rp[g];
-                            const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    __half* yp = p.y + m * p.ldy + n0;
+                    if (full) {
+                        auto add8 = [&](const uint4& u, int g) {
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
                                 const float2 f = unpack_half2(w[t]);
                                 v[g * 8 + t * 2] += f.x;
                                 v[g * 8 + t * 2 + 1] += f.y;
                             }
+                        };
+                        if (p.bias) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) add8(bv[g], g);
+                        }
+                        if (rv_row) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) add8(rvv[g], g);
+                        }
+                        if (p.act == GCB_ACT_SILU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                        }
+                        if (res_row) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) add8(res_cur[g], g);
+                        }
+                        uint4* op = reinterpret_cast<uint4*>(yp);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 o;
+                            o.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]);
+                            o.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
+                            o.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]);
+                            o.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
+                            op[g] = o;
+                        }
+                    } else {
+                        const int nvalid = p.N - n0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < nvalid) {
+                                float o = v[j];
+                                if (p.bias) o += __half2float(p.bias[n0 + j]);
+                                if (rv_row) o += __half2float(rv_row[n0 + j]);
+                                if (p.act == GCB_ACT_SILU) o = silu_f(o);
+                                if (res_row) o += __half2float(res_row[n0 + j]);
+                                yp[j] = __float2half_rn(o);
+                            }
                         }
                     }
-                    uint4* op = reinterpret_cast<uint4*>(yp);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 o;
-                        o.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]);
-                        o.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
-                        o.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]);
-                        o.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
-                        op[g] = o;
-                    }
-                } else {
-                    for (int j = 0; j < nvalid; ++j) {
-                        float o = v[j];
-                        if (p.residual) o += __half2float(p.residual[m * p.ldy + n0 + j]);
-                        yp[j] = __float2half_rn(o);
-                    }
                 }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) res_cur[g] = res_nxt[g];
             }
         } else {
             // GEGLU: tile columns [0, BN/2) = value, [BN/2, BN) = gate; output width N/2
+            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            tc_fence_after();
             const int half_bn = p.BN / 2;
             const int n_out = p.N / 2;
             for (int c = 0; c < half_bn / 32; ++c) {
@@ -312,7 +348,7 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
     p.kb_per_tap = (ksize == 3) ? Cin / BK : gcb_cdiv(Cin, BK);
     p.nkb = taps * p.kb_per_tap;
     const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
-    int budget = 200 * 1024;
+    int budget = 110 * 1024;  // two CTAs per SM: one tile's epilogue overlaps the other's main loop
     if (const char* e = getenv("GCB_GEMM_SMEM_KB")) budget = atoi(e) * 1024;
     p.stages = budget / stage_bytes;
     if (p.stages < 2) p.stages = 2;

@@ -16,43 +16,64 @@ __device__ __forceinline__ const __half* gn_src(const __half* x1, const __half* 
     return c < C1 ? x1 + pix * C1 + c : x2 + pix * C2 + (c - C1);
 }
 
-// partial[b][chunk][g][2] = (sum, sumsq) over the chunk's pixels.  Deterministic: every thread owns fixed
-// (row-group, column-pair) cells and the per-group reduction walks them in a fixed order (no atomics).
-constexpr int GN_MAX_CELLS = 1280 + 256;  // column pairs (C <= 2560) or 256 threads' cells for narrow tensors
+// partial[b][chunk][g][2] = (sum, sumsq) over the chunk's pixels.
+// Thread (row r, column v) owns the 8 channels [8v, 8v+8) of pixels r, r+R, r+2R, ... of the chunk: 16-byte coalesced
+// loads, four (sum, sumsq) pairs in registers (groups always own whole channel pairs).  The block reduction walks the
+// [R][C/2] cells in a fixed order: deterministic, no atomics.
+constexpr int GN_THREADS = 320;
+constexpr int GN_MAX_PAIRS = 1280;  // C <= 2560
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2,
-                                                       float* __restrict__ partial, int HW, int C1, int C2, int groups,
-                                                       int pix_per_chunk) {
-    __shared__ float s_sum[GN_MAX_CELLS], s_sq[GN_MAX_CELLS];
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2,
+                                                              float* __restrict__ partial, int HW, int C1, int C2,
+                                                              int groups, int pix_per_chunk) {
+    __shared__ float s_sum[GN_MAX_PAIRS], s_sq[GN_MAX_PAIRS];
     const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-    const int C = C1 + C2, cols = C / 2, cpg = C / groups;
+    const int C = C1 + C2, cv = C / 8, cpg = C / groups;
+    const int R = cv >= GN_THREADS ? 1 : GN_THREADS / cv;  // pixel rows handled per pass
     const int p0 = chunk * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
-    const int rgroups = cols >= 256 ? 1 : 256 / cols;
-    const int rg = cols >= 256 ? 0 : tid / cols;
-    if (rg < rgroups) {
-        for (int col = cols >= 256 ? tid : tid % cols; col < cols; col += 256) {
-            const int c = col * 2;
-            float sum = 0.f, sq = 0.f;
-            for (int p = p0 + rg; p < p1; p += rgroups) {
-                const long long pix = (long long)b * HW + p;
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(gn_src(x1, x2, C1, C2, pix, c)));
-                sum += f.x + f.y;
-                sq += f.x * f.x + f.y * f.y;
-            }
-            s_sum[rg * cols + col] = sum;
-            s_sq[rg * cols + col] = sq;
-            if (cols < 256) break;
-        }
+    for (int i = tid; i < C / 2; i += GN_THREADS) {
+        s_sum[i] = 0.f;
+        s_sq[i] = 0.f;
     }
     __syncthreads();
-    if (tid < groups) {
-        const int c0 = tid * cpg / 2, c1 = (tid + 1) * cpg / 2;  // cpg is even: groups own whole column pairs
-        float sum = 0.f, sq = 0.f;
-        for (int r = 0; r < rgroups; ++r)
-            for (int col = c0; col < c1; ++col) {
-                sum += s_sum[r * cols + col];
-                sq += s_sq[r * cols + col];
+    // R passes over smem (one row of threads at a time) keep the accumulation order fixed
+    for (int v0 = 0; v0 < cv; v0 += GN_THREADS) {
+        const int r = cv >= GN_THREADS ? 0 : tid / cv;
+        const int v = cv >= GN_THREADS ? v0 + tid : tid % cv;
+        float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool active = r < R && v < cv;
+        if (active) {
+            const int c = v * 8;
+            for (int p = p0 + r; p < p1; p += R) {
+                const long long pix = (long long)b * HW + p;
+                const uint4 raw = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
+                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 f = unpack_half2(w[t]);
+                    sum[t] += f.x + f.y;
+                    sq[t] += f.x * f.x + f.y * f.y;
+                }
             }
+        }
+        for (int rr = 0; rr < R; ++rr) {
+            if (active && r == rr) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    s_sum[v * 4 + t] += sum[t];
+                    s_sq[v * 4 + t] += sq[t];
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < groups) {
+        const int c0 = tid * cpg / 2, c1 = (tid + 1) * cpg / 2;
+        float sum = 0.f, sq = 0.f;
+        for (int col = c0; col < c1; ++col) {
+            sum += s_sum[col];
+            sq += s_sq[col];
+        }
         float* o = partial + (((long long)b * gridDim.x + chunk) * groups + tid) * 2;
         o[0] = sum;
         o[1] = sq;
@@ -194,11 +215,11 @@ extern "C" int gcb_groupnorm_nhwc_fwd(const void* x1, const void* x2, const void
         return GCB_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    int nchunks = gcb_cdiv(HW, 128);
-    if (nchunks > GN_MAX_CHUNKS) nchunks = GN_MAX_CHUNKS;
-    const int ppc = gcb_cdiv(HW, nchunks);
-    nchunks = gcb_cdiv(HW, ppc);
-    gn_stats_kernel<<<dim3(nchunks, B), 256, 0, st>>>((const __half*)x1, (const __half*)x2, (float*)workspace, HW, C1,
+    // chunking depends on HW only (never on B) so that a row's statistics are bit-identical in any batch
+    int ppc = HW <= 16384 ? gcb_cdiv(HW, 64) : gcb_cdiv(HW, GN_MAX_CHUNKS);
+    if (ppc < 16) ppc = 16;
+    const int nchunks = gcb_cdiv(HW, ppc);
+    gn_stats_kernel<<<dim3(nchunks, B), GN_THREADS, 0, st>>>((const __half*)x1, (const __half*)x2, (float*)workspace, HW, C1,
                                                       C2, groups, ppc);
     GCB_LAUNCH_CHECK();
     // apply: ~64 pixels per CTA at C>=1280, more for narrow tensors

@@ -38,6 +38,7 @@ class AttnPlan:
     ref_kv: Optional[Dict[str, torch.Tensor]] = None       # layer name -> qkv tensor of the reference rows
     record_kv: Optional[Dict[str, torch.Tensor]] = None    # if set, every self-attn layer stores its qkv tensor here
     text_index: Optional[torch.Tensor] = None              # [B,1] int32: which prompt embedding each row uses
+    gather: Optional[object] = None                        # callable(layer, qkv_local) -> qkv of ALL reference rows
 
 
 def vanilla_plan(B: int, device, text_index: Optional[torch.Tensor] = None) -> AttnPlan:
@@ -242,9 +243,15 @@ class SD15Denoiser:
         wqkv, _ = net.cat_lin([blk + ".attn1.to_q", blk + ".attn1.to_k", blk + ".attn1.to_v"])
         qkv = ops.linear(n1, wqkv)  # [B,N,3C]
         layer = f"{net_id}:{blk}.attn1"
-        if plan.record_kv is not None:
-            plan.record_kv[layer] = qkv
-        kv2 = plan.ref_kv[layer] if plan.ref_kv is not None else None
+        if plan.gather is not None:
+            # sharded reference pass (parallel.py): all-gather the rows' q|k|v so every reference row sees all references
+            kv2 = plan.gather(layer, qkv)
+            if plan.record_kv is not None:
+                plan.record_kv[layer] = kv2
+        else:
+            if plan.record_kv is not None:
+                plan.record_kv[layer] = qkv
+            kv2 = plan.ref_kv[layer] if plan.ref_kv is not None else None
         weights = plan.weights_unet if net_id == 0 else plan.weights_cnet
         a = ops.attention(qkv, 0, 3 * C, qkv, C, 2 * C, 3 * C, kv2, C, 2 * C, 3 * C, B, N, N, heads, d, plan.src_index,
                           weights)

@@ -76,6 +76,52 @@ class _GraphedStep:
         self.graph.replay()
 
 
+class _ShardedRefStep:
+    """Reference pass of one DDIM step with its 2R CFG rows split across ranks (parallel.py).  Every rank holds the R
+    reference latents; it evaluates the network on its own rows (per-layer K/V all-gather inside), all-gathers the
+    eps rows (32 KB each) and applies the CFG combine + DDIM update to all R latents."""
+
+    def __init__(self, den: SD15Denoiser, R: int, guidance: float, hw: int, world: int, rank: int, gather,
+                 ref_frames: Sequence[int], use_graph: bool):
+        from . import parallel as par
+        dev = den.dev
+        self.den, self.R, self.guidance, self.world, self.rank = den, R, guidance, world, rank
+        self.per = par.padded_rows_per_rank(R, world)
+        self.rows = par.ref_row_partition(R, world, rank)
+        rows = self.rows + [self.rows[-1] if self.rows else 0] * (self.per - len(self.rows))  # pad with a real row
+        self.lat_of_row = torch.tensor([g % R for g in rows], dtype=torch.long, device=dev)
+        src = par.sharded_ref_src_index(R, world, rank, ref_frames)
+        src = src + [src[-1] if src else [-1] * (1 + len(ref_frames))] * (self.per - len(src))
+        K = len(ref_frames)
+        self.rec: Dict[str, torch.Tensor] = {}
+        self.plan = AttnPlan(torch.tensor(src, dtype=torch.int32, device=dev), [0.6] + [0.4 / K] * K,
+                             [0.0] + [1.0 / K] * K, record_kv=self.rec,
+                             text_index=torch.tensor([[g // R] for g in rows], dtype=torch.int32, device=dev),
+                             gather=gather)
+        self.x = torch.zeros((R, hw, hw, 4), dtype=torch.float16, device=dev)
+        self.cond_all = torch.zeros((R, hw, hw, den.ch[0]), dtype=torch.float16, device=dev)
+        self.t = torch.zeros((self.per,), dtype=torch.float32, device=dev)
+        self.coef = torch.zeros((4,), dtype=torch.float32, device=dev)
+        self.eps_all = torch.zeros((world * self.per, hw, hw, 4), dtype=torch.float16, device=dev)
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches = 0
+
+    def set_cond(self, cond_emb: torch.Tensor) -> None:
+        self.cond_all.copy_(cond_emb)
+
+    def _body(self) -> None:
+        import torch.distributed as dist
+        xin = self.x[self.lat_of_row]
+        cond = self.cond_all[self.lat_of_row]
+        eps = self.den.eps(xin, self.t, cond, self.plan)
+        dist.all_gather_into_tensor(self.eps_all, eps.contiguous())
+        R = self.R
+        ops.cfg_ddim_step(self.eps_all[:R], self.eps_all[R:2 * R], self.x, self.guidance, self.coef, out=self.x)
+
+    run = _GraphedStep.run
+
+
 class EditEngine:
     def __init__(self, denoiser: SD15Denoiser, tables: Optional[DDIMTables] = None, use_graphs: bool = True):
         self.den = denoiser
@@ -148,12 +194,15 @@ class EditEngine:
     def edit_refs_once(self, latents: torch.Tensor, disparity: torch.Tensor, ref_indices: Sequence[int],
                        pos_embed: torch.Tensor, neg_embed: torch.Tensor, S: int, guidance: float, view_batch: int = 4,
                        ref_frames: Sequence[int] = (0, 1, 2, 3), view_ids: Optional[Sequence[int]] = None,
-                       ref_exchange: Optional[Callable] = None) -> torch.Tensor:
+                       dist_ctx: Optional[dict] = None) -> torch.Tensor:
         """Edit all V views: latents [V,4,h,w] (z_T of every view), disparity [V,3,H,W], ref_indices = the R reference
         view ids.  Per DDIM step: (1) the R references are denoised once, recording every self-attention layer's
         K/V; (2) the remaining views are denoised in batches of `view_batch`, reading that K/V.
         Reference views' own edited latents are rows of pass (1) (SURVEY §8a gotcha 6).
-        `view_ids`: the subset of views this rank edits (multi-GPU sharding); default all."""
+        `view_ids`: the subset of views this rank edits (multi-GPU sharding); default all.
+        `dist_ctx` = {"world", "rank", "gather": parallel.KVAllGather, "graph_refs": bool}: the reference pass is
+        sharded over the ranks' CFG rows with a per-layer K/V all-gather; result rows of views this rank does not own
+        stay zero (parallel.gather_view_results assembles them)."""
         assert guidance > 1.0
         V, hw = latents.shape[0], latents.shape[-1]
         R = len(ref_indices)
@@ -165,12 +214,18 @@ class EditEngine:
         cond_map = {v: c for v, c in zip(need, self._cond_emb(disparity[need]))}
         # (1) reference pass
         bsz = min(view_batch, max(1, len(non_ref)))
-        key = ("refs_once", R, bsz, hw, float(guidance), tuple(ref_frames))
+        world = dist_ctx["world"] if dist_ctx else 1
+        key = ("refs_once", R, bsz, hw, float(guidance), tuple(ref_frames), world)
         if key not in self._steps:
-            rec0: Dict[str, torch.Tensor] = {}
-            self._steps[key] = [_GraphedStep(self.den, R, True, guidance,
-                                             literal_crossview_plan(R, self.dev, ref_frames, record_kv=rec0), hw,
-                                             self.use_graphs), rec0, None]
+            if world > 1:
+                rs = _ShardedRefStep(self.den, R, guidance, hw, world, dist_ctx["rank"], dist_ctx["gather"], ref_frames,
+                                     self.use_graphs and dist_ctx.get("graph_refs", True))
+                self._steps[key] = [rs, rs.rec, None]
+            else:
+                rec0: Dict[str, torch.Tensor] = {}
+                self._steps[key] = [_GraphedStep(self.den, R, True, guidance,
+                                                 literal_crossview_plan(R, self.dev, ref_frames, record_kv=rec0), hw,
+                                                 self.use_graphs), rec0, None]
         ref_step, rec, view_step = self._steps[key]
         ref_step.x.copy_(x_all[list(ref_indices)])
         ref_step.set_cond(torch.stack([cond_map[v] for v in ref_indices]))
@@ -185,11 +240,13 @@ class EditEngine:
         for t in self.tables.timesteps(S):
             coefs = self.tables.step_coefs(t, S)
             ref_step.run(t, coefs)
-            if ref_exchange is not None:
-                ref_exchange(rec)
             if batches and view_step is None:
-                view_step = _GraphedStep(self.den, bsz, True, guidance,
-                                         cached_crossview_plan(bsz, R, self.dev, rec, ref_frames), hw, self.use_graphs)
+                vplan = cached_crossview_plan(bsz, R, self.dev, rec, ref_frames)
+                if world > 1:
+                    from . import parallel as par
+                    vplan.src_index = torch.tensor(par.view_src_index(bsz, R, world, ref_frames), dtype=torch.int32,
+                                                   device=self.dev)
+                view_step = _GraphedStep(self.den, bsz, True, guidance, vplan, hw, self.use_graphs)
                 self._steps[key][2] = view_step
             for bi in range(len(batches)):
                 view_step.x.copy_(x_views[bi])

@@ -164,21 +164,34 @@ class GaussCtrlPipeline(VanillaPipeline):
                 sel = list(self.ref_indices) + list(range(i, min(V, i + self.chunk_size)))
                 outs.append(self.engine.edit_reference_schedule(z_dev[sel], disparity[sel], pos, neg, S, g, R))
             lat = torch.cat(outs)
+            mine = list(range(V))
         else:
+            dist_ctx, view_ids = None, None
+            mine = list(range(V))
+            if self.world_size > 1:
+                # views shard across ranks, the reference pass shards over its CFG rows (parallel.py); every rank
+                # writes the views it owns into its own train_data, rank 0 also the reference views
+                from . import parallel as par
+                if getattr(self, "_kv_gather", None) is None:
+                    self._kv_gather = par.KVAllGather()
+                rank = torch.distributed.get_rank()
+                dist_ctx = {"world": self.world_size, "rank": rank, "gather": self._kv_gather}
+                view_ids = par.shard_views(V, self.world_size, rank, self.ref_indices)
+                mine = sorted(view_ids + (list(self.ref_indices) if rank == 0 else []))
             lat = self.engine.edit_refs_once(z_dev, disparity, self.ref_indices, pos, neg, S, g,
-                                             view_batch=max(1, self.chunk_size))
+                                             view_batch=max(1, self.chunk_size), view_ids=view_ids, dist_ctx=dist_ctx)
         masks = uned = None
-        if all("mask_image" in d for d in td):
-            masks = torch.from_numpy(np.stack([np.asarray(d["mask_image"], dtype=np.float32) for d in td])).to(dev)
-            uned = torch.stack([d["unedited_image"] for d in td]).to(dev, torch.float16)
+        if all("mask_image" in td[i] for i in mine):
+            masks = torch.from_numpy(np.stack([np.asarray(td[i]["mask_image"], dtype=np.float32) for i in mine])).to(dev)
+            uned = torch.stack([td[i]["unedited_image"] for i in mine]).to(dev, torch.float16)
             self.h2d_bytes += masks.numel() * 4 + uned.numel() * 2
-        imgs = self.vae.decode_latents(lat, masks, uned)               # [V,H,W,3] fp32
+        imgs = self.vae.decode_latents(lat[mine], masks, uned)         # [n,H,W,3] fp32
         host = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=True)
         host.copy_(imgs, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self.d2h_bytes = host.numel() * 4
-        for i in range(V):
-            td[int(td[i].get("image_idx", i))]["image"] = host[i]   # global_idx = image_idx (gc_pipeline.py:224,234)
+        for j, i in enumerate(mine):
+            td[int(td[i].get("image_idx", i))]["image"] = host[j]   # global_idx = image_idx (gc_pipeline.py:224,234)
 
     # ------------------------------------------------------------------------------------------ helpers (same names)
     @torch.no_grad()

@@ -1,0 +1,116 @@
+"""Multi-GPU sharding of the edit stage: one process per GPU, `torch.distributed` (NCCL over NVLink on the GPU box,
+gloo in the CPU tests) for the plumbing.
+
+What shards:
+  * the V views: independent once the reference views' K/V is known - each rank edits `shard_views(...)`;
+  * the reference pass: its 2R CFG rows (uncond x R | cond x R) are split across ranks; every self-attention layer
+    all-gathers the rows' fused q|k|v projections so that each reference row attends to all references and every
+    rank ends up holding the complete reference K/V for its own views.  This is the ONE exchange step of the path
+    ("NCCL all-gather of reference K/V", BASELINE.json north_star); nothing else communicates.
+The reference itself has no multi-GPU code (pipe_device is hard-coded to 'cuda:0', gc_pipeline.py:96)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(V: int, world: int, rank: int, ref_indices: Sequence[int]) -> List[int]:
+    """Non-reference views of this rank (round-robin over the non-reference views so shards differ by <= 1 view).
+    Reference views are produced by the reference pass and reported by the rank that owns their CFG rows' result
+    (rank 0 gathers them)."""
+    refs = set(ref_indices)
+    non_ref = [v for v in range(V) if v not in refs]
+    return non_ref[rank::world]
+
+
+def ref_row_partition(R: int, world: int, rank: int) -> List[int]:
+    """Global CFG-row ids (0..2R-1, layout [uncond x R | cond x R]) of the reference pass owned by `rank`.
+    Rows are dealt contiguously; when world > 2R the extra ranks own no reference row (they still take part in the
+    all-gather with an empty contribution padded to the common size)."""
+    n = 2 * R
+    per = (n + world - 1) // world
+    return [g for g in range(rank * per, min(n, (rank + 1) * per))]
+
+
+def padded_rows_per_rank(R: int, world: int) -> int:
+    return (2 * R + world - 1) // world
+
+
+def sharded_ref_src_index(R: int, world: int, rank: int, ref_frames: Sequence[int] = (0, 1, 2, 3)) -> List[List[int]]:
+    """src_index rows for this rank's reference rows when ALL K/V come from the gathered buffer (negative ids):
+    source 0 = the row itself, sources 1.. = frames `ref_frames` of the row's CFG half.  Gathered row id of global
+    row g is g itself (ranks contribute contiguous, padded blocks: see `gathered_row`)."""
+    per = padded_rows_per_rank(R, world)
+    rows = []
+    for g in ref_row_partition(R, world, rank):
+        half = g // R
+        rows.append([-(gathered_row(g, per) + 1)] + [-(gathered_row(half * R + r, per) + 1) for r in ref_frames])
+    return rows
+
+
+def gathered_row(g: int, per: int) -> int:
+    """Row of global reference row g inside the all-gathered [world*per, ...] buffer (contiguous deal => identity)."""
+    return (g // per) * per + (g % per)
+
+
+def view_src_index(Bv: int, R: int, world: int, ref_frames: Sequence[int] = (0, 1, 2, 3)) -> List[List[int]]:
+    """src_index for a views-only batch [uncond x Bv | cond x Bv] reading reference K/V from the gathered buffer."""
+    per = padded_rows_per_rank(R, world)
+    rows = []
+    for half in range(2):
+        for f in range(Bv):
+            rows.append([half * Bv + f] + [-(gathered_row(half * R + r, per) + 1) for r in ref_frames])
+    return rows
+
+
+class KVAllGather:
+    """All-gather of the reference rows' fused q|k|v projection of one self-attention layer.
+
+    local [per, N, 3C] (rows beyond the rank's real rows are padding) -> gathered [world*per, N, 3C].  Output buffers
+    are cached per layer so that captured CUDA graphs (and the view graphs that read them) see stable addresses."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buffers: Dict[str, torch.Tensor] = {}
+        self.bytes = 0
+
+    def __call__(self, layer: str, local: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return local
+        out = self.buffers.get(layer)
+        shape = (self.world * local.shape[0],) + tuple(local.shape[1:])
+        if out is None or tuple(out.shape) != shape:
+            out = torch.empty(shape, dtype=local.dtype, device=local.device)
+            self.buffers[layer] = out
+        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        self.bytes += out.numel() * out.element_size()
+        return out
+
+
+def gather_view_results(local: torch.Tensor, local_ids: Sequence[int], V: int, world: int,
+                        group: Optional[dist.ProcessGroup] = None) -> Optional[torch.Tensor]:
+    """Collect per-rank results [n_local, ...] into [V, ...] on every rank (64 KB per view for latents).  Ranks may
+    hold different numbers of views: contributions are padded to the maximum."""
+    if world == 1:
+        out = torch.zeros((V,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        out[list(local_ids)] = local
+        return out
+    n_max = torch.tensor([len(local_ids)], device=local.device)
+    dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=group)
+    n_max = int(n_max.item())
+    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: len(local_ids)] = local
+    ids = torch.full((n_max,), -1, dtype=torch.int64, device=local.device)
+    ids[: len(local_ids)] = torch.tensor(list(local_ids), dtype=torch.int64, device=local.device)
+    all_vals = [torch.empty_like(pad) for _ in range(world)]
+    all_ids = [torch.empty_like(ids) for _ in range(world)]
+    dist.all_gather(all_vals, pad, group=group)
+    dist.all_gather(all_ids, ids, group=group)
+    out = torch.zeros((V,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for vals, idv in zip(all_vals, all_ids):
+        keep = idv >= 0
+        out[idv[keep]] = vals[keep]
+    return out

@@ -1,0 +1,108 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in gaussctrl_b200/parallel.py: view sharding, the
+reference-row partition, the K/V all-gather and the source-index tables - checked by evaluating the attention the
+tables describe with the oracle and comparing with the single-process literal cross-view attention."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _attend(q_rows, src_rows, kv_self, kv_gathered, weights, heads):
+    """Evaluate the multi-source attention described by src_index rows with the oracle (CPU fp32)."""
+    from oracle import crossview_attn as cva
+    C = q_rows.shape[-1] // 3
+    outs = []
+    for i, srcs in enumerate(src_rows):
+        ks, vs = [], []
+        for sidx in srcs:
+            buf = kv_gathered[-(sidx + 1)] if sidx < 0 else kv_self[sidx]
+            ks.append(buf[None, :, C:2 * C])
+            vs.append(buf[None, :, 2 * C:])
+        outs.append(cva.multi_source_attention(q_rows[i:i + 1, :, :C], ks, vs, weights, heads))
+    return torch.cat(outs)
+
+
+def _worker(rank, world, port, R, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gaussctrl_b200 import parallel as par
+        from oracle import crossview_attn as cva
+        heads, d, N = 2, 8, 12
+        C = heads * d
+        g = torch.Generator().manual_seed(0)
+        qkv_all = torch.randn((2 * R, N, 3 * C), generator=g)     # reference pass rows [uncond x R | cond x R]
+        per = par.padded_rows_per_rank(R, world)
+        mine = par.ref_row_partition(R, world, rank)
+        local = torch.zeros((per, N, 3 * C))
+        local[: len(mine)] = qkv_all[mine]
+        gather = par.KVAllGather()
+        full = gather("layer0", local)
+        assert full.shape[0] == world * per
+        for gi in range(2 * R):
+            assert torch.equal(full[par.gathered_row(gi, per)], qkv_all[gi])
+        # reference rows: sharded tables == literal 5-pass result of the full batch
+        frames = tuple(range(min(R, 4)))
+        w = [0.6] + [0.4 / len(frames)] * len(frames)
+        ks, vs, ws = cva.crossview_sources(qkv_all[..., C:2 * C], qkv_all[..., 2 * C:], R, frames, 0.6)
+        want = cva.multi_source_attention(qkv_all[..., :C], ks, vs, ws, heads)
+        src = par.sharded_ref_src_index(R, world, rank, frames)
+        got = _attend(qkv_all[mine], src, None, full, w, heads)
+        assert torch.allclose(got, want[mine], atol=1e-6)
+        # view rows of this rank: [uncond x Bv | cond x Bv] reading the gathered reference K/V
+        V = 11
+        ref_idx = [1, 4, 6, 9]
+        views = par.shard_views(V, world, rank, ref_idx)
+        all_views = sorted(sum([par.shard_views(V, world, r, ref_idx) for r in range(world)], []))
+        assert all_views == [v for v in range(V) if v not in ref_idx]
+        Bv = 2
+        gv = torch.Generator().manual_seed(100 + rank)
+        qkv_view = torch.randn((2 * Bv, N, 3 * C), generator=gv)
+        vsrc = par.view_src_index(Bv, R, world, frames)
+        got_v = _attend(qkv_view, vsrc, qkv_view, full, w, heads)
+        # literal: a chunk [refs | views] in the reference's batch layout
+        F = R + Bv
+        chunk = torch.cat([qkv_all[:R], qkv_view[:Bv], qkv_all[R:], qkv_view[Bv:]])
+        ks, vs, ws = cva.crossview_sources(chunk[..., C:2 * C], chunk[..., 2 * C:], F, frames, 0.6)
+        lit = cva.multi_source_attention(chunk[..., :C], ks, vs, ws, heads)
+        want_v = torch.cat([lit[R:F], lit[F + R:]])
+        assert torch.allclose(got_v, want_v, atol=1e-6)
+        # result gather with ragged shards
+        vals = torch.tensor([[float(v)] for v in views])
+        out = par.gather_view_results(vals, views, V, world)
+        for v in range(V):
+            assert out[v, 0].item() == (0.0 if v in ref_idx else float(v))
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("R", [4, 3])
+def test_sharded_reference_pass_tables_world2(tmp_path, R):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, R, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_partition_helpers():
+    from gaussctrl_b200 import parallel as par
+    for R in (1, 3, 4, 8):
+        for world in (1, 2, 3, 4, 8, 16):
+            rows = sum([par.ref_row_partition(R, world, r) for r in range(world)], [])
+            assert rows == list(range(2 * R))
+            per = par.padded_rows_per_rank(R, world)
+            assert all(len(par.ref_row_partition(R, world, r)) <= per for r in range(world))
+    assert par.shard_views(10, 3, 1, [0, 5]) == [2, 6, 9]
