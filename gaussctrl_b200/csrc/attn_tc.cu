@@ -5,18 +5,20 @@
 //
 // One CTA = 256 query rows (two 128-row slots A/B) of one (batch row, head).  Warp roles (320 threads):
 //   warps 0-3 / 4-7 : softmax of slot A / B - one query row per thread, S read from TMEM (tcgen05.ld), exp2 on packed
-//                     halves (ex2.approx.f16x2), P written to shared memory in the 128B-swizzled K-major layout
+//                     halves (ex2.approx.f16x2), P written back to TMEM (tcgen05.st) as the A operand of P V: the
+//                     probabilities never touch shared memory (ncu r1a: shared-memory bandwidth was the limiter)
 //   warp 8          : TMA producer (Q once; K and V tiles of 128 keys through 3-stage mbarrier rings)
 //   warp 9          : TMEM allocator + single-thread tcgen05.mma issuer:
 //                       S   = Q K^T          M128 x N128 x K48  (Q/K tiles are 64-column TMA boxes; columns 40..47 of Q
 //                                                                are zeroed in smem so the neighbouring head's columns
 //                                                                that ride along in K contribute nothing)
 //                       O  += P V            M128 x N48  x K128 (V used MN-major straight from its row-major tile)
-//                       l  += P 1            M128 x N16  x K128 (row sums on the tensor core, fp32 in TMEM)
+//                     (row sums l are accumulated by the softmax threads in fp32: a separate N=16 "P x ones" MMA was
+//                      measured to cost as much issue/latency as the P V product itself)
 // Online softmax with lazy rescaling: the running max only moves when a tile exceeds it by 2^8, so the O/l
 // correction (TMEM load-scale-store) is rare.  Sources are processed back to back; at the end of each source the slot
-// folds O * w_s / l into fp32 registers.  TMEM: S_A[0,128) S_B[128,256) O_A[256,304) l_A[304,320) O_B[320,368)
-// l_B[368,384) acc_A[384,432) acc_B[432,480).
+// folds O * w_s / l into an fp32 shared-memory accumulator.  TMEM: S_A[0,128) S_B[128,256) O_A[256,304) l_A[304,320)
+// O_B[320,368) l_B[368,384) P_A[384,448) P_B[448,512) (P = 128 keys of packed fp16 = 64 columns).
 #include "../../include/gaussctrl_b200.h"
 #include "common.cuh"
 
@@ -26,10 +28,10 @@ constexpr int MAX_SRC = 8;
 constexpr int D = 40;
 constexpr int BM = 128;           // query rows per slot
 constexpr int BN = 128;           // keys per tile
-constexpr int KSTAGES = 3, VSTAGES = 3;
+constexpr int KSTAGES = 4, VSTAGES = 4;
 constexpr uint32_t TILE_BYTES = 128 * 128;  // one 128-row x 64-halves TMA box
 constexpr uint32_t TM_S_A = 0, TM_S_B = 128, TM_O_A = 256, TM_L_A = 304, TM_O_B = 320, TM_L_B = 368;
-constexpr uint32_t TM_ACC_A = 384, TM_ACC_B = 432;  // fp32 running sum over sources (48 columns per slot)
+constexpr uint32_t TM_P_A = 384, TM_P_B = 448;      // packed fp16 probabilities (A operand of P V and of the row sums)
 constexpr float RESCALE_THRESHOLD = 8.f;
 
 struct AttnTcParams {
@@ -48,8 +50,7 @@ struct __align__(1024) Smem {
     uint8_t q[2][TILE_BYTES];
     uint8_t k[KSTAGES][TILE_BYTES];
     uint8_t v[VSTAGES][TILE_BYTES];
-    uint8_t p[2][2][TILE_BYTES];   // [slot][64-key half]
-    uint8_t ones[2048];            // 16 rows x 128 B of fp16 1.0 (B operand of the row-sum MMA; any layout: all ones)
+    float acc[2][D][BM];           // [slot][column][row]: sum over sources of w_s * O_s / l_s
     uint64_t q_full, q_ready;
     uint64_t k_full[KSTAGES], k_empty[KSTAGES], v_full[VSTAGES], v_empty[VSTAGES];
     uint64_t s_full[2], s_free[2], p_ready[2], p_free[2], o_free[2];
@@ -62,6 +63,11 @@ __device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) { mbar_arrive(bar)
 __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
     uint32_t y;
     asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_f32(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
@@ -85,6 +91,21 @@ __device__ __forceinline__ void tmem_ld32_into(uint32_t taddr, uint32_t (&r)[128
         : "r"(taddr)
         : "memory");
 }
+// tcgen05.st 32x32b.x32 from r[OFF .. OFF+31]
+template <int OFF>
+__device__ __forceinline__ void tmem_st32_from(uint32_t taddr, const uint32_t (&r)[128]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[OFF + 0]), "r"(r[OFF + 1]), "r"(r[OFF + 2]), "r"(r[OFF + 3]), "r"(r[OFF + 4]), "r"(r[OFF + 5]),
+          "r"(r[OFF + 6]), "r"(r[OFF + 7]), "r"(r[OFF + 8]), "r"(r[OFF + 9]), "r"(r[OFF + 10]), "r"(r[OFF + 11]),
+          "r"(r[OFF + 12]), "r"(r[OFF + 13]), "r"(r[OFF + 14]), "r"(r[OFF + 15]), "r"(r[OFF + 16]), "r"(r[OFF + 17]),
+          "r"(r[OFF + 18]), "r"(r[OFF + 19]), "r"(r[OFF + 20]), "r"(r[OFF + 21]), "r"(r[OFF + 22]), "r"(r[OFF + 23]),
+          "r"(r[OFF + 24]), "r"(r[OFF + 25]), "r"(r[OFF + 26]), "r"(r[OFF + 27]), "r"(r[OFF + 28]), "r"(r[OFF + 29]),
+          "r"(r[OFF + 30]), "r"(r[OFF + 31])
+        : "memory");
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -97,7 +118,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmV2, const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
     const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int nkt = p.Nk / BN;
     const int T = p.n_act * nkt;  // (source, key tile) pairs, processed in order
@@ -122,8 +143,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         mbar_fence_init();
     }
-    // fp16 ones for the row-sum MMA
-    for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm.ones)[i] = 0x3C003C00u;
     if (warp == 9) {
         tmem_alloc(smem_u32(&sm.tmem_base), 512);
         tmem_relinquish();
@@ -135,8 +154,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tmem = sm.tmem_base;
 
     if (warp == 8) {
-        // ===================================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================================== TMA producer (whole warp walks the loop,
+        // one elected lane issues)
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmK);
             tma_prefetch_desc(&tmV);
@@ -145,53 +165,60 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int qrow = b * p.Nq + qt * 2 * BM;
             tma_load_2d(smem_u32(sm.q[0]), &tmQ, qf, p.q_col0 + head * D, qrow);
             tma_load_2d(smem_u32(sm.q[1]), &tmQ, qf, p.q_col0 + head * D, qrow + BM);
-            for (int i = 0; i < T; ++i) {
-                const int s = i / nkt, j = i - s * nkt;
-                const int sidx = p.src_index[b * p.n_src_total + p.src_id[s]];
-                const bool second = sidx < 0;
-                const int row = (second ? -(sidx + 1) : sidx) * p.Nk + j * BN;
-                {
-                    const int st = i % KSTAGES;
-                    mbar_wait(smem_u32(&sm.k_empty[st]), (((uint32_t)(i / KSTAGES)) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        for (int i = 0; i < T; ++i) {
+            const int s = i / nkt, j = i - s * nkt;
+            const int sidx = p.src_index[b * p.n_src_total + p.src_id[s]];
+            const bool second = sidx < 0;
+            const int row = (second ? -(sidx + 1) : sidx) * p.Nk + j * BN;
+            {
+                const int st = i % KSTAGES;
+                mbar_wait(smem_u32(&sm.k_empty[st]), (((uint32_t)(i / KSTAGES)) & 1u) ^ 1u);
+                if (elect_one_sync()) {
                     const uint32_t fb = smem_u32(&sm.k_full[st]);
                     mbar_expect_tx(fb, TILE_BYTES);
                     tma_load_2d(smem_u32(sm.k[st]), second ? &tmK2 : &tmK, fb, (second ? p.k2_col0 : p.k_col0) + head * D,
                                 row);
                 }
-                {
-                    const int st = i % VSTAGES;
-                    mbar_wait(smem_u32(&sm.v_empty[st]), (((uint32_t)(i / VSTAGES)) & 1u) ^ 1u);
+                __syncwarp();
+            }
+            {
+                const int st = i % VSTAGES;
+                mbar_wait(smem_u32(&sm.v_empty[st]), (((uint32_t)(i / VSTAGES)) & 1u) ^ 1u);
+                if (elect_one_sync()) {
                     const uint32_t fb = smem_u32(&sm.v_full[st]);
                     mbar_expect_tx(fb, TILE_BYTES);
                     tma_load_2d(smem_u32(sm.v[st]), second ? &tmV2 : &tmV, fb, (second ? p.v2_col0 : p.v_col0) + head * D,
                                 row);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 9) {
-        // ===================================================================== MMA issuer (one thread)
-        if (lane == 0) {
+        // ===================================================================== MMA issuer (whole warp waits, one elected
+        // lane issues tcgen05.mma / tcgen05.commit)
+        {
             const uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
             const uint32_t idesc_pv = make_idesc_f16(BM, 48, 0, 1);   // B = V, MN-major
-            const uint32_t idesc_l = make_idesc_f16(BM, 16, 0, 0);
-            const uint64_t ones_desc = make_smem_desc(smem_u32(sm.ones), 16, 1024, 2);
             mbar_wait(smem_u32(&sm.q_ready), 0);
             tc_fence_after();
             auto issue_qk = [&](int t, int i) {
                 const int st = i % KSTAGES;
-                if (t == 0) {
-                    mbar_wait(smem_u32(&sm.k_full[st]), ((uint32_t)(i / KSTAGES)) & 1u);
-                }
+                if (t == 0) mbar_wait(smem_u32(&sm.k_full[st]), ((uint32_t)(i / KSTAGES)) & 1u);
                 if (i > 0) mbar_wait(smem_u32(&sm.s_free[t]), ((uint32_t)(i - 1)) & 1u);
                 tc_fence_after();
-                const uint64_t qd = make_smem_desc(smem_u32(sm.q[t]), 16, 1024, 2);
-                const uint64_t kd = make_smem_desc(smem_u32(sm.k[st]), 16, 1024, 2);
+                if (elect_one_sync()) {
+                    const uint64_t qd = make_smem_desc(smem_u32(sm.q[t]), 16, 1024, 2);
+                    const uint64_t kd = make_smem_desc(smem_u32(sm.k[st]), 16, 1024, 2);
 #pragma unroll
-                for (int ks = 0; ks < 3; ++ks)
-                    tc_mma_ss(tmem + (t ? TM_S_B : TM_S_A), qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_qk,
-                              (uint32_t)(ks != 0));
-                tc_commit(smem_u32(&sm.s_full[t]));
-                if (t == 1) tc_commit(smem_u32(&sm.k_empty[st]));
+                    for (int ks = 0; ks < 3; ++ks)
+                        tc_mma_ss(tmem + (t ? TM_S_B : TM_S_A), qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_qk,
+                                  (uint32_t)(ks != 0));
+                    tc_commit(smem_u32(&sm.s_full[t]));
+                    if (t == 1) tc_commit(smem_u32(&sm.k_empty[st]));
+                }
+                __syncwarp();
             };
             auto issue_pv = [&](int t, int i) {
                 const int s = i / nkt, j = i - s * nkt;
@@ -200,18 +227,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 mbar_wait(smem_u32(&sm.p_ready[t]), ((uint32_t)i) & 1u);
                 if (j == 0 && s > 0) mbar_wait(smem_u32(&sm.o_free[t]), ((uint32_t)(s - 1)) & 1u);
                 tc_fence_after();
-                const uint32_t o_t = tmem + (t ? TM_O_B : TM_O_A), l_t = tmem + (t ? TM_L_B : TM_L_A);
+                if (elect_one_sync()) {
+                    const uint32_t o_t = tmem + (t ? TM_O_B : TM_O_A);
+                    const uint32_t p_t = tmem + (t ? TM_P_B : TM_P_A);
+                    const uint64_t vd0 = make_smem_desc(smem_u32(sm.v[st]), 1024, 1024, 2);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    // A: P [128 x 16 keys] of 64-key half kk/4, 32 B further per k-step; B: V rows (keys) 16*kk.., 128 B each
-                    const uint64_t pd = make_smem_desc(smem_u32(sm.p[t][kk >> 2]) + (uint32_t)((kk & 3) * 32), 16, 1024, 2);
-                    const uint64_t vd = make_smem_desc(smem_u32(sm.v[st]) + (uint32_t)(kk * 2048), 1024, 1024, 2);
-                    const uint32_t acc = (uint32_t)((j | kk) != 0);
-                    tc_mma_ss(o_t, pd, vd, idesc_pv, acc);
-                    tc_mma_ss(l_t, pd, ones_desc, idesc_l, acc);
+                    for (int kk = 0; kk < 8; ++kk) {
+                        // A: P [128 x 16 keys] from TMEM (8 columns of packed halves per k-step);
+                        // B: V rows (keys) 16*kk.. of the row-major tile, 128 B each (MN-major): +2048 B per k-step
+                        tc_mma_ts(o_t, p_t + (uint32_t)(kk * 8), vd0 + (uint64_t)(kk * 128), idesc_pv,
+                                  (uint32_t)((j | kk) != 0));
+                    }
+                    tc_commit(smem_u32(&sm.p_free[t]));
+                    if (t == 1) tc_commit(smem_u32(&sm.v_empty[st]));
                 }
-                tc_commit(smem_u32(&sm.p_free[t]));
-                if (t == 1) tc_commit(smem_u32(&sm.v_empty[st]));
+                __syncwarp();
             };
             issue_qk(0, 0);
             issue_qk(1, 0);
@@ -239,12 +269,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         fence_proxy_async();
         mbar_arrive(smem_u32(&sm.q_ready));
 
-        const uint32_t acc_t = tmem + lane_base + (t ? TM_ACC_B : TM_ACC_A);
-        uint8_t* prow = sm.p[t][0] + (row >> 3) * 1024 + (row & 7) * 128;
-        const int sw = row & 7;
+        const uint32_t p_t = tmem + lane_base + (t ? TM_P_B : TM_P_A);
+        float* acc_row = &sm.acc[t][0][row];
 
         for (int s = 0; s < p.n_act; ++s) {
             float m = -INFINITY;  // running reference max, exp2 domain
+            float l = 0.f;        // running row sum (fp32, of the un-rounded probabilities)
             for (int j = 0; j < nkt; ++j) {
                 const int i = s * nkt + j;
                 mbar_wait(smem_u32(&sm.s_full[t]), ((uint32_t)i) & 1u);
@@ -281,8 +311,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         tc_fence_after();
                         waited = true;
                         const float alpha = grow ? exp2f(m - mx) : 1.f;
+                        l *= alpha;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < 3; ++c) {
                             uint32_t ov[16];
                             tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
                             tc_wait_ld();
@@ -296,24 +327,30 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 // p = 2^(s*scale - m) on packed halves, kept in registers (reusing the score registers) ...
                 const float negm = -m;
+                float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-                for (int e = 0; e < 64; ++e) {
-                    const float x0 = fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm);
-                    const float x1 = fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm);
-                    sr[e] = ex2_f16x2(cvt_f16x2(x0, x1));
+                for (int e = 0; e < 64; e += 2) {
+                    const float p0 = ex2_f32(fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm));
+                    const float p1 = ex2_f32(fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm));
+                    const float p2 = ex2_f32(fmaf(__uint_as_float(sr[2 * e + 2]), p.scale_log2, negm));
+                    const float p3 = ex2_f32(fmaf(__uint_as_float(sr[2 * e + 3]), p.scale_log2, negm));
+                    l0 += p0;
+                    l1 += p1;
+                    l2 += p2;
+                    l3 += p3;
+                    sr[e] = cvt_f16x2(p0, p1);
+                    sr[e + 1] = cvt_f16x2(p2, p3);
                 }
+                l += (l0 + l1) + (l2 + l3);
                 // ... so that the wait for P(i-1) to be consumed by its P V product overlaps the exponentials
                 if (!waited) {
                     mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
                     tc_fence_after();
                 }
-                // K-major SW128 A operand of P V: 16-byte chunk c of the row goes to chunk (c ^ row%8) of its 64-key half
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    uint8_t* dst = prow + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) * 16);
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(sr[c * 4], sr[c * 4 + 1], sr[c * 4 + 2], sr[c * 4 + 3]);
-                }
-                fence_proxy_async();
+                // A operand of P V in TMEM: lane = query row, column e = keys (2e, 2e+1) packed
+                tmem_st32_from<0>(p_t, sr);
+                tmem_st32_from<32>(p_t + 32, sr);
+                tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sm.p_ready[t]));
             }
@@ -321,39 +358,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int ilast = s * nkt + nkt - 1;
             mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)ilast) & 1u);
             tc_fence_after();
-            uint32_t lv[16];
-            tmem_ld_32x32b_x16(o_t + 48, lv);
-            tc_wait_ld();
-            const float wl = p.weight[s] / __uint_as_float(lv[0]);
+            const float wl = p.weight[s] / l;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {   // 48 columns in 3 chunks of 16 (columns 40..47 are don't-care)
-                uint32_t ov[16], av[16];
+            for (int c = 0; c < 3; ++c) {   // 40 columns in chunks of 16
+                uint32_t ov[16];
                 tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
-                if (s > 0) tmem_ld_32x32b_x16(acc_t + (uint32_t)(c * 16), av);
                 tc_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const float prev = s > 0 ? __uint_as_float(av[e]) : 0.f;
-                    av[e] = __float_as_uint(fmaf(__uint_as_float(ov[e]), wl, prev));
+                    const int col = c * 16 + e;
+                    if (col < D) {
+                        const float prev = s > 0 ? acc_row[col * BM] : 0.f;
+                        acc_row[col * BM] = fmaf(__uint_as_float(ov[e]), wl, prev);
+                    }
                 }
-                tmem_st_32x32b_x16(acc_t + (uint32_t)(c * 16), av);
             }
-            tc_wait_st();
             tc_fence_before();
             mbar_arrive(smem_u32(&sm.o_free[t]));
         }
         // ---- store the row: 40 halves = 5 x 16 B
-        float oacc[48];
-        {
-            uint32_t a0[32], a1[16];
-            tmem_ld_32x32b_x32(acc_t, a0);
-            tmem_ld_32x32b_x16(acc_t + 32, a1);
-            tc_wait_ld();
+        float oacc[D];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) oacc[c] = __uint_as_float(a0[c]);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) oacc[32 + c] = __uint_as_float(a1[c]);
-        }
+        for (int c = 0; c < D; ++c) oacc[c] = acc_row[c * BM];
         const long long grow_ = (long long)b * p.Nq + qt * 2 * BM + t * BM + row;
         uint4* dst = reinterpret_cast<uint4*>(p.out + grow_ * p.ld_out + head * D);
 #pragma unroll

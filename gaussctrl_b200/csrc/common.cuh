@@ -63,6 +63,23 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
+// ---- warp-uniform role dispatch --------------------------------------------------------------------------------
+// The warp index is broadcast with a shuffle so the compiler can prove the role branches warp-uniform, and the single
+// issuing lane is picked with elect.sync.  Without this (e.g. `if (lane == 0)`), every tcgen05.mma / TMA instruction -
+// which take uniform-register operands - is wrapped in an ELECT/R2UR "waterfall" loop (seen in the r1 SASS), costing
+// ~50 issue cycles per MMA.
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, %1;\n\t"
+        "@P1 mov.s32 %0, 1;\n\t}"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

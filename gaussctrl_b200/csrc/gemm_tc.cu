@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x, m_tile = blockIdx.y;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_stage_bytes = (uint32_t)p.BN * BK * 2;
@@ -72,30 +72,33 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        if (lane == 0) {
+        // ---------------- TMA producer: the whole warp walks the ring, one elected lane issues ----------------
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
-            int b0 = 0, h0 = 0, w0 = 0;
-            if (p.mode == 1) {
-                if (p.HW >= BM) {
-                    const int tiles_per_img = p.HW / BM;
-                    b0 = m_tile / tiles_per_img;
-                    const int r = m_tile % tiles_per_img;
-                    if (p.W >= BM) {
-                        const int segs = p.W / BM;
-                        h0 = r / segs;
-                        w0 = (r % segs) * BM;
-                    } else {
-                        h0 = r * p.bh;
-                    }
+        }
+        int b0 = 0, h0 = 0, w0 = 0;
+        if (p.mode == 1) {
+            if (p.HW >= BM) {
+                const int tiles_per_img = p.HW / BM;
+                b0 = m_tile / tiles_per_img;
+                const int r = m_tile % tiles_per_img;
+                if (p.W >= BM) {
+                    const int segs = p.W / BM;
+                    h0 = r / segs;
+                    w0 = (r % segs) * BM;
                 } else {
-                    b0 = m_tile * p.bb;
+                    h0 = r * p.bh;
                 }
+            } else {
+                b0 = m_tile * p.bb;
             }
-            for (int kb = 0; kb < p.nkb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        }
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+            if (elect_one_sync()) {
                 const uint32_t fb = smem_u32(&full_bar[s]);
                 mbar_expect_tx(fb, stage_bytes);
                 const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
@@ -109,14 +112,16 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 }
                 tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * p.BN);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            for (int kb = 0; kb < p.nkb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(smem_u32(&full_bar[s]), ph);
-                tc_fence_after();
+        // ---------------- MMA issuer: whole warp waits, one elected lane issues tcgen05.mma / commit ----------------
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+            mbar_wait(smem_u32(&full_bar[s]), ph);
+            tc_fence_after();
+            if (elect_one_sync()) {
                 const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
                 const uint32_t sb = sa + A_STAGE_BYTES;
                 const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
@@ -128,8 +133,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                               (uint32_t)((kb | k) != 0));
                 }
                 tc_commit(smem_u32(&empty_bar[s]));
+                if (kb == p.nkb - 1) tc_commit(smem_u32(&tmem_full_bar));
             }
-            tc_commit(smem_u32(&tmem_full_bar));
+            __syncwarp();
         }
     } else {
         // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------

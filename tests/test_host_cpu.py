@@ -1,0 +1,132 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol the header declares, the host-side tables
+(parameter spec, DDIM tables, reference-view selection, attention source tables) equal the oracle / the reference's
+golden vectors, and the product refuses to run without a CUDA device instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, REPO
+
+
+def test_library_exports_every_declared_symbol():
+    from gaussctrl_b200 import _lib
+    hdr = open(os.path.join(REPO, "include", "gaussctrl_b200.h")).read()
+    declared = set(re.findall(r"\b(gcb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/gaussctrl_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.gcb_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    """Host-side checks run before any CUDA call: bad arguments return GCB_ERR_INVALID with a message."""
+    from gaussctrl_b200 import _lib
+    lib = _lib.lib
+    rc = lib.gcb_conv2d_nhwc_fwd(None, None, None, None, 0, None, None, 1, 1, 1, 8, 8, 1, 0, 0, None)
+    assert rc == -1 and b"null" in lib.gcb_last_error()
+    assert lib.gcb_geglu_tile_n(2560) == 256 and lib.gcb_geglu_tile_n(128) == 128
+    perm = (ctypes.c_int32 * 512)()
+    assert lib.gcb_geglu_pack_rows(512, perm) == 0
+    p = list(perm)
+    assert sorted(p) == list(range(512)) and p[:3] == [0, 1, 2] and p[128] == 256  # value|gate halves per 256 tile
+    assert lib.gcb_scan_workspace_bytes(1 << 20) > 0 and lib.gcb_depth_order_workspace_bytes(1000) > 4000
+
+
+def test_no_cpu_fallback():
+    from gaussctrl_b200 import _lib, ops
+    x = torch.zeros((1, 8, 8, 8), dtype=torch.float16)
+    with pytest.raises(_lib.GcbError):
+        ops.silu(x)
+    # nothing in the product package imports the oracle
+    pkg = os.path.join(REPO, "gaussctrl_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_parameter_spec_matches_oracle_modules():
+    from gaussctrl_b200 import sd15_spec as sp
+    from oracle import sd15
+    for mod, shapes in ((sd15.UNet2DConditionModel(), sp.unet_shapes()), (sd15.ControlNetModel(), sp.controlnet_shapes()),
+                        (sd15.AutoencoderKL(), sp.vae_shapes())):
+        assert {k: tuple(v.shape) for k, v in mod.state_dict().items()} == shapes
+    assert sum(int(np.prod(s)) for s in sp.unet_shapes().values()) == 859_520_964  # SD1.x UNet parameter count
+
+
+def test_ddim_tables_match_oracle():
+    from gaussctrl_b200.sd15_spec import DDIMTables
+    from oracle import sd15
+    mine, ref = DDIMTables(), sd15.DDIMTables()
+    for S in (4, 20, 50):
+        assert mine.timesteps(S) == ref.timesteps(S).tolist()
+        assert mine.inverse_timesteps(S) == ref.inverse_timesteps(S).tolist()
+        g = torch.Generator().manual_seed(S)
+        x, eps = torch.randn(64, generator=g), torch.randn(64, generator=g)
+        for t in mine.timesteps(S)[::5]:
+            sa, s1a, sp_, s1p = mine.step_coefs(t, S)
+            assert torch.allclose(sp_ * (x - s1a * eps) / sa + s1p * eps, ref.step(eps, t, x, S), atol=1e-5)
+            sa, s1a, sp_, s1p = mine.inverse_step_coefs(t, S)
+            assert torch.allclose(sp_ * (x - s1a * eps) / sa + s1p * eps, ref.inverse_step(eps, t, x, S), atol=1e-5)
+    # inverse o forward with an exact eps oracle returns the input (closed-form check)
+    S, t = 20, 501
+    sa, s1a, sp_, s1p = mine.step_coefs(t, S)
+    x, eps = torch.randn(16), torch.randn(16)
+    y = sp_ * (x - s1a * eps) / sa + s1p * eps
+    ia, i1a, ip, i1p = mine.inverse_step_coefs(t, S)
+    assert torch.allclose(ip * (y - i1a * eps) / ia + i1p * eps, x, atol=1e-5)
+
+
+def test_ref_index_selection_matches_reference_golden():
+    from gaussctrl_b200.gc_pipeline import select_ref_indices
+    z = np.load(os.path.join(GOLDEN, "glue_reference.npz"))
+    n = 0
+    for key in z.files:
+        if key.startswith("ref_indices."):
+            _, v, r = key.split(".")
+            V = int(v[1:])
+            assert select_ref_indices(V, int(r[1:])) == [min(i, V - 1) for i in z[key].tolist()]
+            n += 1
+    assert n >= 3
+    assert select_ref_indices(40, 4) == [4, 11, 29, 31]          # SURVEY §8a gotcha 3
+    assert select_ref_indices(1, 1) == [0]                        # the reference returns [1] (out of range)
+
+
+def test_attention_source_tables():
+    from gaussctrl_b200.diffusion import cached_crossview_plan, literal_crossview_plan, vanilla_plan
+    p = literal_crossview_plan(7, "cpu")
+    assert p.src_index.tolist()[0] == [0, 0, 1, 2, 3] and p.src_index.tolist()[7 + 5] == [12, 7, 8, 9, 10]
+    assert p.weights_unet == [0.6, 0.1, 0.1, 0.1, 0.1] and p.weights_cnet == [0.0, 0.25, 0.25, 0.25, 0.25]
+    assert p.text_index.reshape(-1).tolist() == [0] * 7 + [1] * 7
+    c = cached_crossview_plan(3, 4, "cpu", {})
+    assert c.src_index.tolist()[0] == [0, -1, -2, -3, -4] and c.src_index.tolist()[4] == [4, -5, -6, -7, -8]
+    assert vanilla_plan(3, "cpu").src_index.reshape(-1).tolist() == [0, 1, 2]
+
+
+def test_compat_cameras_and_model_shell():
+    from gaussctrl_b200._compat import Cameras
+    from gaussctrl_b200.gc_model import GaussCtrlModel, GaussCtrlModelConfig, projection_matrix, viewmat_from_c2w
+    from oracle import gsplat_ref as gr
+    cams = Cameras(torch.eye(4)[:3].repeat(5, 1, 1), 500.0, 501.0, 256.0, 255.0, 512, 512)
+    assert len(cams) == 5 and cams[2].shape == (1,) and int(cams[3].width.item()) == 512
+    c2w = torch.tensor([[0.36, -0.48, 0.8, 1.0], [0.8, 0.6, 0.0, 2.0], [-0.48, 0.64, 0.6, 3.0]])
+    assert torch.equal(viewmat_from_c2w(c2w), gr.viewmat_from_c2w(torch.cat([c2w, torch.tensor([[0, 0, 0, 1.0]])])))
+    assert torch.equal(projection_matrix(0.001, 1000, 0.9, 0.8), gr.projection_matrix(0.001, 1000, 0.9, 0.8))
+    m = GaussCtrlModel(GaussCtrlModelConfig(), num_points=10)
+    assert set(dict(m.named_parameters())) == {"means", "scales", "quats", "features_dc", "features_rest", "opacities"}
+    cfg = GaussCtrlModelConfig()
+    assert (cfg.use_lpips, cfg.use_l1, cfg.patch_size, cfg.lpips_loss_mult) == (True, True, 32, 1.0)
+
+
+def test_pipeline_config_defaults_match_reference():
+    """Field names / defaults of gaussctrl/gc_pipeline.py:48-73."""
+    from gaussctrl_b200.gc_pipeline import GaussCtrlPipelineConfig
+    c = GaussCtrlPipelineConfig()
+    assert (c.render_rate, c.edit_prompt, c.reverse_prompt, c.langsam_obj, c.guidance_scale, c.num_inference_steps,
+            c.chunk_size, c.ref_view_num, c.diffusion_ckpt) == (500, "", "", "", 5, 20, 5, 4, "CompVis/stable-diffusion-v1-4")
