@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--views", type=int, default=40, help="views per GPU (bear-like scene: 40)")
     ap.add_argument("--gaussians", type=int, default=1_000_000)
     ap.add_argument("--ddim-steps", type=int, default=S_STEPS)
+    ap.add_argument("--view-batch", type=int, default=12,
+                    help="views denoised per launch in the refs-once schedule (results do not depend on it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -188,6 +190,7 @@ def main():
                                   num_inference_steps=S, chunk_size=CHUNK, ref_view_num=REFS)
     pipe = GaussCtrlPipeline(cfg, dev, world_size=world, local_rank=local, datamanager=dm, model=model,
                              weights=synthetic_weights(0))
+    pipe.view_batch = args.view_batch
 
     # ---- stage-A products (untimed setup): rasterise depth for the ControlNet condition; z_T ~ N(0,1)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -220,7 +223,7 @@ def main():
         mine = sorted(view_ids + (list(pipe.ref_indices) if rank == 0 else []))
 
     def device_step():
-        lat = pipe.engine.edit_refs_once(z_dev, disparity, pipe.ref_indices, pos, neg, S, GUIDANCE, view_batch=CHUNK,
+        lat = pipe.engine.edit_refs_once(z_dev, disparity, pipe.ref_indices, pos, neg, S, GUIDANCE, view_batch=args.view_batch,
                                          view_ids=view_ids, dist_ctx=dist_ctx)
         return pipe.vae.decode_latents(lat[mine])
 
@@ -254,6 +257,18 @@ def main():
     ms_per_step = ms / args.steps
     value = V / (ms_per_step / 1e3)
 
+    # ---- breakdown of one step (untimed extra): denoising loop vs VAE decode
+    e0, e1, e2 = ev(), ev(), ev()
+    torch.cuda.synchronize()
+    e0.record()
+    lat_b = pipe.engine.edit_refs_once(z_dev, disparity, pipe.ref_indices, pos, neg, S, GUIDANCE,
+                                       view_batch=args.view_batch, view_ids=view_ids, dist_ctx=dist_ctx)
+    e1.record()
+    pipe.vae.decode_latents(lat_b[mine])
+    e2.record()
+    torch.cuda.synchronize()
+    breakdown = {"denoise_ms": e0.elapsed_time(e1), "vae_decode_ms": e1.elapsed_time(e2)}
+
     # ---- e2e through the public API: host train_data -> edit_images() -> host images
     e2e = None
     if not args.no_e2e:
@@ -272,10 +287,11 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        Bq, C = 2 * CHUNK, ATTN_C
+        Bq, C = 2 * args.view_batch, ATTN_C
         qkv = torch.randn((Bq, ATTN_N, 3 * C), device=dev).half()
         refkv = torch.randn((2 * REFS, ATTN_N, 3 * C), device=dev).half()
-        rows = [[h * CHUNK + f] + [-(h * REFS + r) - 1 for r in range(4)] for h in range(2) for f in range(CHUNK)]
+        vb = args.view_batch
+        rows = [[h * vb + f] + [-(h * REFS + r) - 1 for r in range(4)] for h in range(2) for f in range(vb)]
         idx = torch.tensor(rows, dtype=torch.int32, device=dev)
         w = [0.6, 0.1, 0.1, 0.1, 0.1]
         call = lambda: ops.attention(qkv, 0, 3 * C, qkv, C, 2 * C, 3 * C, refkv, C, 2 * C, 3 * C, Bq, ATTN_N, ATTN_N,  # noqa: E731
@@ -315,6 +331,7 @@ def main():
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "extra": {"raster_ms_per_view_median": raster_ms[len(raster_ms) // 2] if raster_ms else None,
                           "schedule": "refs_once (reference views denoised once per DDIM step, K/V recorded)",
+                          "view_batch": args.view_batch, "breakdown": breakdown,
                           "views_total": V,
                           "multi_gpu": None if world == 1 else "views sharded round-robin; reference pass sharded over "
                                        "its 2R CFG rows with a per-layer NCCL all-gather of q|k|v"}}

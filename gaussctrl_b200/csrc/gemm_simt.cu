@@ -138,6 +138,67 @@ __global__ void conv_direct_kernel(const __half* __restrict__ x, const __half* _
     }
 }
 
+// 3x3 stride-1 pad-1 convolution with a tiny input channel count (conv_in 4->320 of UNet/ControlNet, VAE conv_in):
+// one CTA = 64 output pixels x all Cout; weights [K=9*Cin][Cout] and the pixels' input patches live in shared memory;
+// a thread owns two adjacent output channels (half2 weights, coalesced half2 stores).
+constexpr int SC_PIX = 64;
+__global__ void __launch_bounds__(256) conv_small_cin_kernel(const __half* __restrict__ x, const __half* __restrict__ w,
+                                                             const __half* __restrict__ bias,
+                                                             const __half* __restrict__ residual,
+                                                             __half* __restrict__ y, int B, int H, int W, int Cin,
+                                                             int Cout, int act) {
+    extern __shared__ __align__(16) uint8_t sc_smem[];
+    const int K = 9 * Cin, cp = Cout / 2;
+    __half2* ws = reinterpret_cast<__half2*>(sc_smem);                     // [K][cp]
+    float* xs = reinterpret_cast<float*>(sc_smem + (size_t)K * cp * 4);    // [SC_PIX][K]
+    const long long npix = (long long)B * H * W;
+    const long long p0 = (long long)blockIdx.x * SC_PIX;
+    for (int i = threadIdx.x; i < K * cp; i += blockDim.x) {
+        const int k = i / cp, c2 = i % cp;
+        ws[i] = __halves2half2(w[(long long)(2 * c2) * K + k], w[(long long)(2 * c2 + 1) * K + k]);
+    }
+    for (int i = threadIdx.x; i < SC_PIX * K; i += blockDim.x) {
+        const int pl = i / K, k = i % K;
+        const long long pix = p0 + pl;
+        float v = 0.f;
+        if (pix < npix) {
+            const int tap = k / Cin, ci = k % Cin;
+            const int wq = (int)(pix % W), hq = (int)((pix / W) % H);
+            const long long b = pix / ((long long)W * H);
+            const int hi = hq + tap / 3 - 1, wi = wq + tap % 3 - 1;
+            if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __half2float(x[((b * H + hi) * W + wi) * Cin + ci]);
+        }
+        xs[i] = v;
+    }
+    __syncthreads();
+    const int groups = blockDim.x / cp;  // pixel groups working in parallel
+    const int g = threadIdx.x / cp, c2 = threadIdx.x % cp;
+    if (g >= groups) return;
+    float2 bv = make_float2(0.f, 0.f);
+    if (bias) bv = __half22float2(*reinterpret_cast<const __half2*>(bias + 2 * c2));
+    for (int pl = g; pl < SC_PIX; pl += groups) {
+        const long long pix = p0 + pl;
+        if (pix >= npix) break;
+        float a0 = bv.x, a1 = bv.y;
+        const float* xr = xs + pl * K;
+        for (int k = 0; k < K; ++k) {
+            const float2 wf = __half22float2(ws[k * cp + c2]);
+            a0 = fmaf(xr[k], wf.x, a0);
+            a1 = fmaf(xr[k], wf.y, a1);
+        }
+        if (act == GCB_ACT_SILU) {
+            a0 = silu_f(a0);
+            a1 = silu_f(a1);
+        }
+        if (residual) {
+            const float2 r = __half22float2(*reinterpret_cast<const __half2*>(residual + pix * Cout + 2 * c2));
+            a0 += r.x;
+            a1 += r.y;
+        }
+        *reinterpret_cast<__half2*>(y + pix * Cout + 2 * c2) = __floats2half2_rn(a0, a1);
+    }
+}
+
 __global__ void im2col3x3_s2_kernel(const __half* __restrict__ x, __half* __restrict__ col, int B, int H, int W, int C,
                                     int pad_lo, int Ho, int Wo) {
     const int cv = C / 8;
@@ -197,6 +258,22 @@ extern "C" int gcb_conv2d_direct_nhwc_fwd(const void* x, const void* w, const vo
     GCB_CHECK_ARG(stride == 1 || stride == 2, "stride must be 1 or 2");
     GCB_CHECK_ARG(act == GCB_ACT_NONE || act == GCB_ACT_SILU, "unsupported act");
     const int Ho = (H + pad_lo + pad_hi - ksize) / stride + 1, Wo = (W + pad_lo + pad_hi - ksize) / stride + 1;
+    if (ksize == 3 && stride == 1 && pad_lo == 1 && pad_hi == 1 && Cin <= 8 && Cout % 2 == 0 && Cout >= 64 && Cout <= 512) {
+        const int cp = Cout / 2, K = 9 * Cin;
+        const int threads_sc = cp >= 256 ? cp : (256 / cp) * cp;
+        const size_t smem = (size_t)K * cp * 4 + (size_t)SC_PIX * K * 4;
+        static size_t configured = 0;
+        if (smem > configured) {
+            GCB_CUDA(cudaFuncSetAttribute(conv_small_cin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            configured = 100 * 1024;
+        }
+        const long long npix = (long long)B * H * W;
+        conv_small_cin_kernel<<<(unsigned)((npix + SC_PIX - 1) / SC_PIX), threads_sc, smem, (cudaStream_t)stream>>>(
+            (const __half*)x, (const __half*)w, (const __half*)bias, (const __half*)residual, (__half*)y, B, H, W, Cin,
+            Cout, act);
+        GCB_LAUNCH_CHECK();
+        return GCB_OK;
+    }
     const long long total = (long long)B * Ho * Wo * Cout;
     const int threads = 256;
     const int blocks = (int)((total + threads - 1) / threads < 148ll * 64 ? (total + threads - 1) / threads : 148ll * 64);

@@ -109,6 +109,18 @@ class PackedNet:
             self._cache[key] = (wp, self._t(name + ".bias"), k)
         return self._cache[key]
 
+    def conv_pad_out(self, name: str, cout: int):
+        """conv weights with the output channels zero-padded to `cout` -> (w [cout, k*k*Cin], bias [cout])"""
+        key = "convpad:" + name
+        if key not in self._cache:
+            w, b, _ = self.conv(name)
+            wp = torch.zeros((cout, w.shape[1]), dtype=torch.float16, device=self.dev)
+            bp = torch.zeros((cout,), dtype=torch.float16, device=self.dev)
+            wp[: w.shape[0]] = w
+            bp[: b.shape[0]] = b
+            self._cache[key] = (wp, bp)
+        return self._cache[key]
+
     def conv_split(self, name: str, c1: int):
         """1x1 conv over a channel concat, split into the two K ranges -> (w1, w2, bias)"""
         key = "convsplit:" + name
@@ -328,5 +340,6 @@ class SD15Denoiser:
                 w, b, _ = un.conv(f"up_blocks.{i}.upsamplers.0.conv")
                 h = ops.conv2d(ops.upsample_nearest2x(h), w, b, 3)
         h = ops.groupnorm(h, None, un.vec("conv_norm_out.weight"), un.vec("conv_norm_out.bias"), 32, 1e-5, True)
-        w, b, _ = un.conv("conv_out")
-        return ops.conv2d_direct(h, w, b, 3, 1, (1, 1), GCB_ACT_NONE)
+        # conv_out (C0 -> 4): run on the tensor-core GEMM with the 4 output channels zero-padded to 8
+        w8, b8 = un.conv_pad_out("conv_out", 8)
+        return ops.conv2d(h, w8, b8, 3)[..., :4].contiguous()

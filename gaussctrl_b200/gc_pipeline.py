@@ -179,7 +179,8 @@ class GaussCtrlPipeline(VanillaPipeline):
                 view_ids = par.shard_views(V, self.world_size, rank, self.ref_indices)
                 mine = sorted(view_ids + (list(self.ref_indices) if rank == 0 else []))
             lat = self.engine.edit_refs_once(z_dev, disparity, self.ref_indices, pos, neg, S, g,
-                                             view_batch=max(1, self.chunk_size), view_ids=view_ids, dist_ctx=dist_ctx)
+                                             view_batch=max(1, getattr(self, "view_batch", self.chunk_size)), view_ids=view_ids,
+                                             dist_ctx=dist_ctx)
         masks = uned = None
         if all("mask_image" in td[i] for i in mine):
             masks = torch.from_numpy(np.stack([np.asarray(td[i]["mask_image"], dtype=np.float32) for i in mine])).to(dev)

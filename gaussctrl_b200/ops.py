@@ -15,6 +15,7 @@ from ._lib import (GCB_ACT_GEGLU, GCB_ACT_NONE, GCB_ACT_SILU, GCB_ATTN_AUTO, GCB
                    lib)
 
 LAUNCHES = [0]  # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
+GEMM_LOG = None  # set to a list to record (B, H, W, Cin, Cout, ksize, act) of every conv2d call (profiling aid)
 
 _GEMM_IMPL = [GCB_GEMM_TCGEN05]
 _ATTN_IMPL = [GCB_ATTN_AUTO]
@@ -58,6 +59,8 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], ksize
     y = out if out is not None else torch.empty((B, H, W, co), dtype=torch.float16, device=x.device)
     if residual is not None:
         assert residual.shape == y.shape and residual.is_contiguous()
+    if GEMM_LOG is not None:
+        GEMM_LOG.append((B, H, W, Cin, Cout, ksize, act))
     check(lib.gcb_conv2d_nhwc_fwd(_p(x), _p(w), _p(bias), _p(rowvec, rowvec_off), rowvec_ld, _p(residual), _p(y), B, H, W,
                                   Cin, Cout, ksize, act, _GEMM_IMPL[0], _stream()))
     LAUNCHES[0] += 1

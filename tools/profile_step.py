@@ -28,8 +28,12 @@ for it in range(reps + 1):  # first iteration = warm-up (weight packing, cudaFun
     if it == 1:
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_push("profiled")
+        ops.GEMM_LOG = []
     e_ref = den.eps(x_ref, t_ref, torch.cat([cond_ref, cond_ref]), ref_plan)
     view_plan = cached_crossview_plan(c, R, "cuda", rec)
     e_view = den.eps(x_view, t_view, torch.cat([cond_view, cond_view]), view_plan)
 torch.cuda.synchronize()
+import json
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(ops.GEMM_LOG, open("gpurun_out/gemm_log.json", "w"))
 print("launches", ops.LAUNCHES[0], "eps", float(e_view.float().abs().mean()))
