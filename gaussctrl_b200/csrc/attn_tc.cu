@@ -1,44 +1,53 @@
-// Multi-source (cross-view) attention on the 5th-gen tensor cores, head dim 40 (the SD1.x 64x64 level: 75 % of the
-// attention FLOPs of the hot path).
+// Multi-source (cross-view) attention on the 5th-gen tensor cores for head dims 40 and 80 (the SD1.x 64x64 and 32x32
+// levels: ~90 % of the attention FLOPs of the hot path).
 //
 //   out[b, i, h, :] = sum_s w_s * softmax_j( q[b,i,h,:] . K_s[j,h,:] * scale ) V_s[j,h,:]      (utils.py:25-37, 88-117)
 //
 // One CTA = 256 query rows (two 128-row slots A/B) of one (batch row, head).  Warp roles (320 threads):
-//   warps 0-3 / 4-7 : softmax of slot A / B - one query row per thread, S read from TMEM (tcgen05.ld), exp2 on packed
-//                     halves (ex2.approx.f16x2), P written back to TMEM (tcgen05.st) as the A operand of P V: the
-//                     probabilities never touch shared memory (ncu r1a: shared-memory bandwidth was the limiter)
-//   warp 8          : TMA producer (Q once; K and V tiles of 128 keys through 3-stage mbarrier rings)
-//   warp 9          : TMEM allocator + single-thread tcgen05.mma issuer:
-//                       S   = Q K^T          M128 x N128 x K48  (Q/K tiles are 64-column TMA boxes; columns 40..47 of Q
-//                                                                are zeroed in smem so the neighbouring head's columns
-//                                                                that ride along in K contribute nothing)
-//                       O  += P V            M128 x N48  x K128 (V used MN-major straight from its row-major tile)
-//                     (row sums l are accumulated by the softmax threads in fp32: a separate N=16 "P x ones" MMA was
-//                      measured to cost as much issue/latency as the P V product itself)
-// Online softmax with lazy rescaling: the running max only moves when a tile exceeds it by 2^8, so the O/l
-// correction (TMEM load-scale-store) is rare.  Sources are processed back to back; at the end of each source the slot
-// folds O * w_s / l into an fp32 shared-memory accumulator.  TMEM: S_A[0,128) S_B[128,256) O_A[256,304) l_A[304,320)
-// O_B[320,368) l_B[368,384) P_A[384,448) P_B[448,512) (P = 128 keys of packed fp16 = 64 columns).
+//   warps 0-3 / 4-7 : softmax of slot A / B - one query row per thread, S read from TMEM (tcgen05.ld), exp2 on the
+//                     MUFU, row sums in fp32 registers, P written back to TMEM (tcgen05.st) as packed halves: the
+//                     A operand of P V.  Probabilities never touch shared memory or HBM.
+//   warp 8          : TMA producer (Q once; K and V tiles of BN keys through 4-stage mbarrier rings)
+//   warp 9          : TMEM allocator + tcgen05.mma issuer (one elected lane):
+//                       S   = Q K^T    M128 x N(BN) x K(DK)   both operands K-major, 128B-swizzled 64-column TMA boxes
+//                       O  += P V      M128 x N(NV) x K(BN)   A = P from TMEM, B = V MN-major straight from its row-major tile
+// Head dim 40: BN=128, DK=48 - the Q/K boxes are 64 columns wide; columns 40..47 of Q are zeroed in smem so the
+//   neighbouring head's columns that ride along in K contribute nothing; NV=48 (columns 40..47 of O are don't-care).
+// Head dim 80: BN=64, DK=80 (two boxes: 64 + 16 used columns), NV=80 (two MN atoms of V).
+// Online softmax with lazy rescaling (threshold 2^8): the O correction (TMEM load-scale-store) is rare.  Sources are
+// processed back to back; at the end of each source the slot folds O * w_s / l into an fp32 accumulator (shared
+// memory for d=40, TMEM for d=80 - whichever the budget of 512 columns / 227 KB leaves room for).
+// ncu history (profiles/): r1a P through shared memory + a separate "P x ones" row-sum MMA, every MMA wrapped in an
+// ELECT waterfall loop: 277 TFLOP/s; r1c (this structure): 440-500 TFLOP/s at d=40.
 #include "../../include/gaussctrl_b200.h"
 #include "common.cuh"
 
 namespace {
 
 constexpr int MAX_SRC = 8;
-constexpr int D = 40;
-constexpr int BM = 128;           // query rows per slot
-constexpr int BN = 128;           // keys per tile
-constexpr int KSTAGES = 4, VSTAGES = 4;
-constexpr uint32_t TILE_BYTES = 128 * 128;  // one 128-row x 64-halves TMA box
-constexpr uint32_t TM_S_A = 0, TM_S_B = 128, TM_O_A = 256, TM_L_A = 304, TM_O_B = 320, TM_L_B = 368;
-constexpr uint32_t TM_P_A = 384, TM_P_B = 448;      // packed fp16 probabilities (A operand of P V and of the row sums)
+constexpr int BM = 128;  // query rows per slot
+constexpr int STAGES = 4;
 constexpr float RESCALE_THRESHOLD = 8.f;
+
+template <int D_>
+struct Cfg;
+template <>
+struct Cfg<40> {
+    static constexpr int D = 40, BN = 128, DK = 48, NV = 48, BOXES = 1;
+    static constexpr bool ZERO_Q_PAD = true, ACC_IN_TMEM = false;
+    static constexpr uint32_t TM_S = 0, TM_O = 256, TM_O_STRIDE = 64, TM_P = 384, TM_ACC = 0;
+};
+template <>
+struct Cfg<80> {
+    static constexpr int D = 80, BN = 64, DK = 80, NV = 80, BOXES = 2;
+    static constexpr bool ZERO_Q_PAD = false, ACC_IN_TMEM = true;
+    static constexpr uint32_t TM_S = 0, TM_O = 128, TM_O_STRIDE = 80, TM_P = 288, TM_ACC = 352;
+};
 
 struct AttnTcParams {
     __half* out;
     int ld_out;
     int Nq, Nk, heads;
-    int q_col0, k_col0, v_col0, k2_col0, v2_col0;  // column of head 0 inside each tensor map
     int n_src_total, n_act;
     int src_id[MAX_SRC];
     float weight[MAX_SRC];
@@ -46,25 +55,21 @@ struct AttnTcParams {
     float scale_log2;
 };
 
+template <int D_>
 struct __align__(1024) Smem {
-    uint8_t q[2][TILE_BYTES];
-    uint8_t k[KSTAGES][TILE_BYTES];
-    uint8_t v[VSTAGES][TILE_BYTES];
-    float acc[2][D][BM];           // [slot][column][row]: sum over sources of w_s * O_s / l_s
+    using C = Cfg<D_>;
+    static constexpr uint32_t QBOX = BM * 128, KVBOX = C::BN * 128;
+    uint8_t q[2][C::BOXES][QBOX];
+    uint8_t k[STAGES][C::BOXES][KVBOX];
+    uint8_t v[STAGES][C::BOXES][KVBOX];
+    float acc[C::ACC_IN_TMEM ? 1 : 2][C::ACC_IN_TMEM ? 1 : C::D][C::ACC_IN_TMEM ? 4 : BM];  // [slot][column][row]
     uint64_t q_full, q_ready;
-    uint64_t k_full[KSTAGES], k_empty[KSTAGES], v_full[VSTAGES], v_empty[VSTAGES];
+    uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
     uint64_t s_full[2], s_free[2], p_ready[2], p_free[2], o_free[2];
     uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar) { mbar_arrive(bar); }
-
-__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
-    uint32_t y;
-    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-    return y;
-}
 __device__ __forceinline__ float ex2_f32(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -75,9 +80,14 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
     return y;
 }
-// tcgen05.ld 32x32b.x32 straight into r[OFF .. OFF+31] (no staging copy)
-template <int OFF>
-__device__ __forceinline__ void tmem_ld32_into(uint32_t taddr, uint32_t (&r)[128]) {
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// tcgen05.ld / st 32x32b.x32 straight into / from r[OFF .. OFF+31] (no staging copies)
+template <int OFF, int NR>
+__device__ __forceinline__ void tmem_ld32_into(uint32_t taddr, uint32_t (&r)[NR]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -91,9 +101,8 @@ __device__ __forceinline__ void tmem_ld32_into(uint32_t taddr, uint32_t (&r)[128
         : "r"(taddr)
         : "memory");
 }
-// tcgen05.st 32x32b.x32 from r[OFF .. OFF+31]
-template <int OFF>
-__device__ __forceinline__ void tmem_st32_from(uint32_t taddr, const uint32_t (&r)[128]) {
+template <int OFF, int NR>
+__device__ __forceinline__ void tmem_st32_from(uint32_t taddr, const uint32_t (&r)[NR]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -106,18 +115,19 @@ __device__ __forceinline__ void tmem_st32_from(uint32_t taddr, const uint32_t (&
           "r"(r[OFF + 30]), "r"(r[OFF + 31])
         : "memory");
 }
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-    float d;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
 
+template <int D_>
 __global__ void __launch_bounds__(320, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
                const __grid_constant__ CUtensorMap tmV2, const AttnTcParams p) {
+    using C = Cfg<D_>;
+    using SM = Smem<D_>;
+    constexpr int D = C::D, BN = C::BN, BOXES = C::BOXES;
+    constexpr int KSTEPS = C::DK / 16, PV_STEPS = BN / 16, PCOLS = BN / 2;
+    constexpr uint32_t STAGE_BYTES = BOXES * SM::KVBOX;
     extern __shared__ uint8_t smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    SM& sm = *reinterpret_cast<SM*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
     const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int nkt = p.Nk / BN;
@@ -126,11 +136,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&sm.q_full), 1);
         mbar_init(smem_u32(&sm.q_ready), 256);
-        for (int i = 0; i < KSTAGES; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             mbar_init(smem_u32(&sm.k_full[i]), 1);
             mbar_init(smem_u32(&sm.k_empty[i]), 1);
-        }
-        for (int i = 0; i < VSTAGES; ++i) {
             mbar_init(smem_u32(&sm.v_full[i]), 1);
             mbar_init(smem_u32(&sm.v_empty[i]), 1);
         }
@@ -147,7 +155,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_alloc(smem_u32(&sm.tmem_base), 512);
         tmem_relinquish();
     }
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -161,10 +168,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tma_prefetch_desc(&tmK);
             tma_prefetch_desc(&tmV);
             const uint32_t qf = smem_u32(&sm.q_full);
-            mbar_expect_tx(qf, 2 * TILE_BYTES);
+            mbar_expect_tx(qf, 2 * BOXES * SM::QBOX);
             const int qrow = b * p.Nq + qt * 2 * BM;
-            tma_load_2d(smem_u32(sm.q[0]), &tmQ, qf, p.q_col0 + head * D, qrow);
-            tma_load_2d(smem_u32(sm.q[1]), &tmQ, qf, p.q_col0 + head * D, qrow + BM);
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int bx = 0; bx < BOXES; ++bx)
+                    tma_load_2d(smem_u32(sm.q[t][bx]), &tmQ, qf, head * D + bx * 64, qrow + t * BM);
         }
         __syncwarp();
         for (int i = 0; i < T; ++i) {
@@ -172,105 +182,99 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int sidx = p.src_index[b * p.n_src_total + p.src_id[s]];
             const bool second = sidx < 0;
             const int row = (second ? -(sidx + 1) : sidx) * p.Nk + j * BN;
-            {
-                const int st = i % KSTAGES;
-                mbar_wait(smem_u32(&sm.k_empty[st]), (((uint32_t)(i / KSTAGES)) & 1u) ^ 1u);
-                if (elect_one_sync()) {
-                    const uint32_t fb = smem_u32(&sm.k_full[st]);
-                    mbar_expect_tx(fb, TILE_BYTES);
-                    tma_load_2d(smem_u32(sm.k[st]), second ? &tmK2 : &tmK, fb, (second ? p.k2_col0 : p.k_col0) + head * D,
-                                row);
-                }
-                __syncwarp();
+            const int st = i % STAGES;
+            const uint32_t par = (((uint32_t)(i / STAGES)) & 1u) ^ 1u;
+            mbar_wait(smem_u32(&sm.k_empty[st]), par);
+            if (elect_one_sync()) {
+                const uint32_t fb = smem_u32(&sm.k_full[st]);
+                mbar_expect_tx(fb, STAGE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < BOXES; ++bx)
+                    tma_load_2d(smem_u32(sm.k[st][bx]), second ? &tmK2 : &tmK, fb, head * D + bx * 64, row);
             }
-            {
-                const int st = i % VSTAGES;
-                mbar_wait(smem_u32(&sm.v_empty[st]), (((uint32_t)(i / VSTAGES)) & 1u) ^ 1u);
-                if (elect_one_sync()) {
-                    const uint32_t fb = smem_u32(&sm.v_full[st]);
-                    mbar_expect_tx(fb, TILE_BYTES);
-                    tma_load_2d(smem_u32(sm.v[st]), second ? &tmV2 : &tmV, fb, (second ? p.v2_col0 : p.v_col0) + head * D,
-                                row);
-                }
-                __syncwarp();
+            __syncwarp();
+            mbar_wait(smem_u32(&sm.v_empty[st]), par);
+            if (elect_one_sync()) {
+                const uint32_t fb = smem_u32(&sm.v_full[st]);
+                mbar_expect_tx(fb, STAGE_BYTES);
+#pragma unroll
+                for (int bx = 0; bx < BOXES; ++bx)
+                    tma_load_2d(smem_u32(sm.v[st][bx]), second ? &tmV2 : &tmV, fb, head * D + bx * 64, row);
             }
+            __syncwarp();
         }
     } else if (warp == 9) {
         // ===================================================================== MMA issuer (whole warp waits, one elected
         // lane issues tcgen05.mma / tcgen05.commit)
-        {
-            const uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
-            const uint32_t idesc_pv = make_idesc_f16(BM, 48, 0, 1);   // B = V, MN-major
-            mbar_wait(smem_u32(&sm.q_ready), 0);
+        const uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
+        const uint32_t idesc_pv = make_idesc_f16(BM, C::NV, 0, 1);  // B = V, MN-major
+        mbar_wait(smem_u32(&sm.q_ready), 0);
+        tc_fence_after();
+        auto issue_qk = [&](int t, int i) {
+            const int st = i % STAGES;
+            if (t == 0) mbar_wait(smem_u32(&sm.k_full[st]), ((uint32_t)(i / STAGES)) & 1u);
+            if (i > 0) mbar_wait(smem_u32(&sm.s_free[t]), ((uint32_t)(i - 1)) & 1u);
             tc_fence_after();
-            auto issue_qk = [&](int t, int i) {
-                const int st = i % KSTAGES;
-                if (t == 0) mbar_wait(smem_u32(&sm.k_full[st]), ((uint32_t)(i / KSTAGES)) & 1u);
-                if (i > 0) mbar_wait(smem_u32(&sm.s_free[t]), ((uint32_t)(i - 1)) & 1u);
-                tc_fence_after();
-                if (elect_one_sync()) {
-                    const uint64_t qd = make_smem_desc(smem_u32(sm.q[t]), 16, 1024, 2);
-                    const uint64_t kd = make_smem_desc(smem_u32(sm.k[st]), 16, 1024, 2);
+            if (elect_one_sync()) {
 #pragma unroll
-                    for (int ks = 0; ks < 3; ++ks)
-                        tc_mma_ss(tmem + (t ? TM_S_B : TM_S_A), qd + (uint64_t)(ks * 2), kd + (uint64_t)(ks * 2), idesc_qk,
-                                  (uint32_t)(ks != 0));
-                    tc_commit(smem_u32(&sm.s_full[t]));
-                    if (t == 1) tc_commit(smem_u32(&sm.k_empty[st]));
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    // 16 halves = 32 B per k-step inside a 64-column box (4 k-steps per box)
+                    const uint64_t qd = make_smem_desc(smem_u32(sm.q[t][ks >> 2]) + (uint32_t)((ks & 3) * 32), 16, 1024, 2);
+                    const uint64_t kd = make_smem_desc(smem_u32(sm.k[st][ks >> 2]) + (uint32_t)((ks & 3) * 32), 16, 1024, 2);
+                    tc_mma_ss(tmem + C::TM_S + (uint32_t)(t * BN), qd, kd, idesc_qk, (uint32_t)(ks != 0));
                 }
-                __syncwarp();
-            };
-            auto issue_pv = [&](int t, int i) {
-                const int s = i / nkt, j = i - s * nkt;
-                const int st = i % VSTAGES;
-                if (t == 0) mbar_wait(smem_u32(&sm.v_full[st]), ((uint32_t)(i / VSTAGES)) & 1u);
-                mbar_wait(smem_u32(&sm.p_ready[t]), ((uint32_t)i) & 1u);
-                if (j == 0 && s > 0) mbar_wait(smem_u32(&sm.o_free[t]), ((uint32_t)(s - 1)) & 1u);
-                tc_fence_after();
-                if (elect_one_sync()) {
-                    const uint32_t o_t = tmem + (t ? TM_O_B : TM_O_A);
-                    const uint32_t p_t = tmem + (t ? TM_P_B : TM_P_A);
-                    const uint64_t vd0 = make_smem_desc(smem_u32(sm.v[st]), 1024, 1024, 2);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        // A: P [128 x 16 keys] from TMEM (8 columns of packed halves per k-step);
-                        // B: V rows (keys) 16*kk.. of the row-major tile, 128 B each (MN-major): +2048 B per k-step
-                        tc_mma_ts(o_t, p_t + (uint32_t)(kk * 8), vd0 + (uint64_t)(kk * 128), idesc_pv,
-                                  (uint32_t)((j | kk) != 0));
-                    }
-                    tc_commit(smem_u32(&sm.p_free[t]));
-                    if (t == 1) tc_commit(smem_u32(&sm.v_empty[st]));
-                }
-                __syncwarp();
-            };
-            issue_qk(0, 0);
-            issue_qk(1, 0);
-            for (int i = 0; i < T; ++i) {
-                if (i + 1 < T) issue_qk(0, i + 1);
-                issue_pv(0, i);
-                if (i + 1 < T) issue_qk(1, i + 1);
-                issue_pv(1, i);
+                tc_commit(smem_u32(&sm.s_full[t]));
+                if (t == 1) tc_commit(smem_u32(&sm.k_empty[st]));
             }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int t, int i) {
+            const int s = i / nkt, j = i - s * nkt;
+            const int st = i % STAGES;
+            if (t == 0) mbar_wait(smem_u32(&sm.v_full[st]), ((uint32_t)(i / STAGES)) & 1u);
+            mbar_wait(smem_u32(&sm.p_ready[t]), ((uint32_t)i) & 1u);
+            if (j == 0 && s > 0) mbar_wait(smem_u32(&sm.o_free[t]), ((uint32_t)(s - 1)) & 1u);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint32_t o_t = tmem + C::TM_O + (uint32_t)(t * C::TM_O_STRIDE);
+                const uint32_t p_t = tmem + C::TM_P + (uint32_t)(t * PCOLS);
+                // V row-major tile = MN-major B: 8-key groups 1024 B apart (SBO), 64-column atoms one box apart (LBO)
+                const uint64_t vd0 = make_smem_desc(smem_u32(sm.v[st][0]), SM::KVBOX, 1024, 2);
+#pragma unroll
+                for (int kk = 0; kk < PV_STEPS; ++kk)
+                    tc_mma_ts(o_t, p_t + (uint32_t)(kk * 8), vd0 + (uint64_t)(kk * 128), idesc_pv, (uint32_t)((j | kk) != 0));
+                tc_commit(smem_u32(&sm.p_free[t]));
+                if (t == 1) tc_commit(smem_u32(&sm.v_empty[st]));
+            }
+            __syncwarp();
+        };
+        issue_qk(0, 0);
+        issue_qk(1, 0);
+        for (int i = 0; i < T; ++i) {
+            if (i + 1 < T) issue_qk(0, i + 1);
+            issue_pv(0, i);
+            if (i + 1 < T) issue_qk(1, i + 1);
+            issue_pv(1, i);
         }
     } else {
         // ===================================================================== softmax slots
-        const int t = warp >> 2;            // slot
-        const int wq = warp & 3;            // TMEM lane quarter
-        const int row = wq * 32 + lane;     // row inside the slot
+        const int t = warp >> 2;         // slot
+        const int wq = warp & 3;         // TMEM lane quarter
+        const int row = wq * 32 + lane;  // row inside the slot
         const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
-        const uint32_t s_t = tmem + lane_base + (t ? TM_S_B : TM_S_A);
-        const uint32_t o_t = tmem + lane_base + (t ? TM_O_B : TM_O_A);  // O[0,48) then l[48,64)
-        // zero Q columns 40..47 (16-byte chunk 5 of the 128B-swizzled row), then publish Q to the MMA thread
+        const uint32_t s_t = tmem + lane_base + C::TM_S + (uint32_t)(t * BN);
+        const uint32_t o_t = tmem + lane_base + C::TM_O + (uint32_t)(t * C::TM_O_STRIDE);
+        const uint32_t p_t = tmem + lane_base + C::TM_P + (uint32_t)(t * PCOLS);
+        const uint32_t acc_t = tmem + lane_base + C::TM_ACC + (uint32_t)(t * 80);
+        float* acc_row = &sm.acc[C::ACC_IN_TMEM ? 0 : t][0][C::ACC_IN_TMEM ? 0 : row];
         mbar_wait(smem_u32(&sm.q_full), 0);
-        {
-            uint8_t* qrow = sm.q[t] + (row >> 3) * 1024 + (row & 7) * 128 + ((5 ^ (row & 7)) * 16);
+        if (C::ZERO_Q_PAD) {
+            // zero Q columns 40..47: 16-byte chunk 5 of the 128B-swizzled row
+            uint8_t* qrow = sm.q[t][0] + (row >> 3) * 1024 + (row & 7) * 128 + ((5 ^ (row & 7)) * 16);
             *reinterpret_cast<uint4*>(qrow) = make_uint4(0, 0, 0, 0);
+            fence_proxy_async();
         }
-        fence_proxy_async();
         mbar_arrive(smem_u32(&sm.q_ready));
-
-        const uint32_t p_t = tmem + lane_base + (t ? TM_P_B : TM_P_A);
-        float* acc_row = &sm.acc[t][0][row];
 
         for (int s = 0; s < p.n_act; ++s) {
             float m = -INFINITY;  // running reference max, exp2 domain
@@ -279,11 +283,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const int i = s * nkt + j;
                 mbar_wait(smem_u32(&sm.s_full[t]), ((uint32_t)i) & 1u);
                 tc_fence_after();
-                uint32_t sr[128];
+                uint32_t sr[BN];
                 tmem_ld32_into<0>(s_t, sr);
                 tmem_ld32_into<32>(s_t + 32, sr);
-                tmem_ld32_into<64>(s_t + 64, sr);
-                tmem_ld32_into<96>(s_t + 96, sr);
+                if (BN == 128) {
+                    tmem_ld32_into<(BN == 128 ? 64 : 0)>(s_t + 64, sr);
+                    tmem_ld32_into<(BN == 128 ? 96 : 0)>(s_t + 96, sr);
+                }
                 tc_wait_ld();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sm.s_free[t]));
@@ -291,10 +297,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 float mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
                       mxd = __uint_as_float(sr[3]);
 #pragma unroll
-                for (int e = 4; e < 128; e += 8) {
+                for (int e = 4; e < BN; e += 8) {
                     mxa = fmax3(mxa, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
                     mxb = fmax3(mxb, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
-                    if (e + 4 < 128) {
+                    if (e + 4 < BN) {
                         mxc = fmax3(mxc, __uint_as_float(sr[e + 4]), __uint_as_float(sr[e + 5]));
                         mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
                     }
@@ -313,7 +319,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         const float alpha = grow ? exp2f(m - mx) : 1.f;
                         l *= alpha;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
+                        for (int c = 0; c < C::NV / 16; ++c) {
                             uint32_t ov[16];
                             tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
                             tc_wait_ld();
@@ -325,11 +331,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         if (grow) m = mx;
                     }
                 }
-                // p = 2^(s*scale - m) on packed halves, kept in registers (reusing the score registers) ...
+                // p = 2^(s*scale - m), kept in registers as packed halves (reusing the score registers) ...
                 const float negm = -m;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-                for (int e = 0; e < 64; e += 2) {
+                for (int e = 0; e < BN / 2; e += 2) {
                     const float p0 = ex2_f32(fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm));
                     const float p1 = ex2_f32(fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm));
                     const float p2 = ex2_f32(fmaf(__uint_as_float(sr[2 * e + 2]), p.scale_log2, negm));
@@ -349,47 +355,64 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 // A operand of P V in TMEM: lane = query row, column e = keys (2e, 2e+1) packed
                 tmem_st32_from<0>(p_t, sr);
-                tmem_st32_from<32>(p_t + 32, sr);
+                if (BN == 128) tmem_st32_from<(BN == 128 ? 32 : 0)>(p_t + 32, sr);
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sm.p_ready[t]));
             }
-            // ---- end of source: out += w_s * O / l
+            // ---- end of source: acc += w_s * O / l
             const int ilast = s * nkt + nkt - 1;
             mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)ilast) & 1u);
             tc_fence_after();
             const float wl = p.weight[s] / l;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {   // 40 columns in chunks of 16
-                uint32_t ov[16];
+            for (int c = 0; c < C::NV / 16; ++c) {
+                uint32_t ov[16], av[16];
                 tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                if (C::ACC_IN_TMEM && s > 0) tmem_ld_32x32b_x16(acc_t + (uint32_t)(c * 16), av);
                 tc_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const int col = c * 16 + e;
-                    if (col < D) {
-                        const float prev = s > 0 ? acc_row[col * BM] : 0.f;
-                        acc_row[col * BM] = fmaf(__uint_as_float(ov[e]), wl, prev);
+                    if (C::ACC_IN_TMEM) {
+                        av[e] = __float_as_uint(fmaf(__uint_as_float(ov[e]), wl, s > 0 ? __uint_as_float(av[e]) : 0.f));
+                    } else if (col < D) {
+                        acc_row[col * BM] = fmaf(__uint_as_float(ov[e]), wl, s > 0 ? acc_row[col * BM] : 0.f);
                     }
                 }
+                if (C::ACC_IN_TMEM) tmem_st_32x32b_x16(acc_t + (uint32_t)(c * 16), av);
             }
+            if (C::ACC_IN_TMEM) tc_wait_st();
             tc_fence_before();
             mbar_arrive(smem_u32(&sm.o_free[t]));
         }
-        // ---- store the row: 40 halves = 5 x 16 B
-        float oacc[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) oacc[c] = acc_row[c * BM];
+        // ---- store the row: D halves = D/8 x 16 B
         const long long grow_ = (long long)b * p.Nq + qt * 2 * BM + t * BM + row;
         uint4* dst = reinterpret_cast<uint4*>(p.out + grow_ * p.ld_out + head * D);
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            uint4 o;
-            o.x = pack_half2(oacc[c * 8 + 0], oacc[c * 8 + 1]);
-            o.y = pack_half2(oacc[c * 8 + 2], oacc[c * 8 + 3]);
-            o.z = pack_half2(oacc[c * 8 + 4], oacc[c * 8 + 5]);
-            o.w = pack_half2(oacc[c * 8 + 6], oacc[c * 8 + 7]);
-            dst[c] = o;
+        for (int c = 0; c < (D + 15) / 16; ++c) {
+            float o16[16];
+            if (C::ACC_IN_TMEM) {
+                uint32_t av[16];
+                tmem_ld_32x32b_x16(acc_t + (uint32_t)(c * 16), av);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o16[e] = __uint_as_float(av[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o16[e] = (c * 16 + e < D) ? acc_row[(c * 16 + e) * BM] : 0.f;
+            }
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+                if (c * 16 + h8 * 8 < D) {
+                    uint4 o;
+                    o.x = pack_half2(o16[h8 * 8 + 0], o16[h8 * 8 + 1]);
+                    o.y = pack_half2(o16[h8 * 8 + 2], o16[h8 * 8 + 3]);
+                    o.z = pack_half2(o16[h8 * 8 + 4], o16[h8 * 8 + 5]);
+                    o.w = pack_half2(o16[h8 * 8 + 6], o16[h8 * 8 + 7]);
+                    dst[c * 2 + h8] = o;
+                }
+            }
         }
     }
     tc_fence_before();
@@ -397,24 +420,59 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
-int encode_rows(CUtensorMap* tm, const void* base, int ld, long long rows, int width) {
+int encode_rows(CUtensorMap* tm, const void* base, int ld, long long rows, int width, int box_rows) {
     const uint64_t dims[2] = {(uint64_t)width, (uint64_t)rows};
     const uint64_t strides[1] = {(uint64_t)ld * 2};
-    const uint32_t box[2] = {64, 128};
+    const uint32_t box[2] = {64, (uint32_t)box_rows};
     return gcb_encode_tma(tm, base, 2, dims, strides, box, 1);
+}
+
+template <int D_>
+int launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2, const void* v2, int ld_kv2,
+           int B, int Nq, int heads, const AttnTcParams& p, cudaStream_t stream) {
+    using C = Cfg<D_>;
+    // tensor maps: inner extent = heads*d columns from each base pointer (columns beyond are zero-filled by TMA, so the
+    // 64-wide boxes of the last head never read past their tensor).  The batch-row count of the K/V buffers is not
+    // part of the ABI: rows are addressed through src_index, the row extent is left open.
+    const int width = heads * C::D;
+    const long long big = 1ll << 31;
+    CUtensorMap tmQ, tmK, tmV, tmK2, tmV2;
+    int rc;
+    if ((rc = encode_rows(&tmQ, q, ld_q, (long long)B * Nq, width, BM))) return rc;
+    if ((rc = encode_rows(&tmK, k, ld_kv, big, width, C::BN))) return rc;
+    if ((rc = encode_rows(&tmV, v, ld_kv, big, width, C::BN))) return rc;
+    if (k2) {
+        if ((rc = encode_rows(&tmK2, k2, ld_kv2, big, width, C::BN))) return rc;
+        if ((rc = encode_rows(&tmV2, v2, ld_kv2, big, width, C::BN))) return rc;
+    } else {
+        tmK2 = tmK;
+        tmV2 = tmV;
+    }
+    const size_t smem = sizeof(Smem<D_>) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        GCB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(Nq / (2 * BM), heads, B);
+    attn_tc_kernel<D_><<<grid, 320, smem, stream>>>(tmQ, tmK, tmV, tmK2, tmV2, p);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
 }
 
 }  // namespace
 
 int gcb_attn_tc_supported(int Nq, int Nk, int heads, int d) {
     (void)heads;
-    return d == D && Nq % (2 * BM) == 0 && Nk % BN == 0 && Nk >= BN;
+    if (Nq % (2 * BM) != 0) return 0;
+    if (d == 40) return Nk % Cfg<40>::BN == 0 && Nk >= Cfg<40>::BN;
+    if (d == 80) return Nk % Cfg<80>::BN == 0 && Nk >= Cfg<80>::BN;
+    return 0;
 }
 
 int gcb_attn_tc_launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2, const void* v2,
                        int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d, int n_src,
                        const int32_t* src_index, const float* h_src_weight, float scale, cudaStream_t stream) {
-    (void)d;
     AttnTcParams p;
     memset(&p, 0, sizeof(p));
     p.out = (__half*)out;
@@ -438,31 +496,8 @@ int gcb_attn_tc_launch(const void* q, int ld_q, const void* k, const void* v, in
     GCB_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
                       ((uintptr_t)out % 16) == 0 && ld_out % 8 == 0,
                   "tcgen05 attention needs 16-byte aligned q/k/v/out");
-    // tensor maps: inner extent = heads*d columns from each base pointer (columns beyond are zero-filled by TMA, so the
-    // 64-wide box of the last head never reads past its tensor).  The batch-row count of the K/V buffers is not part
-    // of the ABI: rows are addressed through src_index, extent is left open.
-    const int width = heads * D;
-    const long long big = 1ll << 31;
-    CUtensorMap tmQ, tmK, tmV, tmK2, tmV2;
-    int rc;
-    if ((rc = encode_rows(&tmQ, q, ld_q, (long long)B * Nq, width))) return rc;
-    if ((rc = encode_rows(&tmK, k, ld_kv, big, width))) return rc;
-    if ((rc = encode_rows(&tmV, v, ld_kv, big, width))) return rc;
-    if (k2) {
-        if ((rc = encode_rows(&tmK2, k2, ld_kv2, big, width))) return rc;
-        if ((rc = encode_rows(&tmV2, v2, ld_kv2, big, width))) return rc;
-    } else {
-        tmK2 = tmK;
-        tmV2 = tmV;
-    }
-    const size_t smem = sizeof(Smem) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        GCB_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    dim3 grid(Nq / (2 * BM), heads, B);
-    attn_tc_kernel<<<grid, 320, smem, stream>>>(tmQ, tmK, tmV, tmK2, tmV2, p);
-    GCB_LAUNCH_CHECK();
-    return GCB_OK;
+    if (d == 40) return launch<40>(q, ld_q, k, v, ld_kv, k2, v2, ld_kv2, B, Nq, heads, p, stream);
+    if (d == 80) return launch<80>(q, ld_q, k, v, ld_kv, k2, v2, ld_kv2, B, Nq, heads, p, stream);
+    gcb_set_error("tcgen05 attention: head dim %d not built", d);
+    return GCB_ERR_UNSUPPORTED;
 }

@@ -329,14 +329,15 @@ def test_batch_invariance(ops):
     assert torch.equal(a_full[:b], a_part)
 
 
-@pytest.mark.parametrize("case", [(4, 512, 1.0), (6, 1024, 1.0), (4, 256, 1.0), (4, 512, 6.0)])
-def test_tcgen05_attention_d40(ops, case):
-    """The tcgen05/TMEM multi-source kernel (head dim 40) vs the oracle and vs the mma.sync kernel: literal layout
+@pytest.mark.parametrize("case", [(4, 512, 1.0, 40), (6, 1024, 1.0, 40), (4, 256, 1.0, 40), (4, 512, 6.0, 40),
+                                  (4, 256, 1.0, 80), (6, 1024, 1.0, 80), (4, 512, 6.0, 80)])
+def test_tcgen05_attention(ops, case):
+    """The tcgen05/TMEM multi-source kernel (head dims 40, 80) vs the oracle and vs the mma.sync kernel: literal layout
     (sources in the same buffer), cached-reference layout (second buffer), and the ControlNet weights (self weight 0).
     `amp` > 1 scales q so that score ranges exceed the lazy-rescale threshold (2^8) and the O/l correction path runs."""
     from oracle import crossview_attn as cva
-    B, N, amp = case
-    heads, d = 8, 40
+    B, N, amp, d = case
+    heads = 8
     C = heads * d
     F = B // 2
     qkv = _rand((B, N, 3 * C), 11)

@@ -25,7 +25,7 @@ def run(Bq, N, C, heads, impl, reps=20):
     t = e0.elapsed_time(e1) / reps / 1e3
     return t, Bq * 5 * 4.0 * N * N * C / t / 1e12
 
-for (Bq, N, C) in [(6, 4096, 320), (8, 4096, 320), (6, 1024, 640), (6, 256, 1280)]:
+for (Bq, N, C) in [(8, 4096, 320), (24, 4096, 320), (8, 1024, 640), (24, 1024, 640), (24, 256, 1280)]:
     for impl, name in ((1, "tcgen05"), (2, "mma.sync")):
         r = run(Bq, N, C, 8, impl)
         if r: print(f"B={Bq} N={N} C={C} {name}: {r[0]*1e3:.3f} ms  {r[1]:.1f} TFLOP/s")
