@@ -33,7 +33,7 @@ SIGNATURES = {
     "gcb_groupnorm_nhwc_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P,
                                        c_size_t, _P]),
     "gcb_layernorm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, _P]),
-    "gcb_attn_multi_fwd": (c_int, [_P, c_int, _P, _P, c_int, _P, _P, c_int, _P, c_int] + [c_int] * 6 +
+    "gcb_attn_multi_fwd": (c_int, [_P, c_int, _P, _P, c_int, _P, _P, c_int, _P, c_int] + [c_int] * 7 +
                            [_P, _FP, c_float, c_int, _P]),
     "gcb_softmax_rows_fwd": (c_int, [_P, _P, c_int, c_int, c_float, _P]),
     "gcb_silu_fwd": (c_int, [_P, _P, c_longlong, _P]),

@@ -23,7 +23,7 @@ struct AttnParams {
     const __half* v2;
     __half* out;
     int ld_q, ld_kv, ld_kv2, ld_out;
-    int B, Nq, Nk, heads;
+    int B, Nq, Nk, heads, vstride;
     int n_src_total;         // stride of src_index per batch row
     int n_act;               // active (non-zero weight) sources
     int src_id[MAX_SRC];     // original source slot of each active source
@@ -102,12 +102,12 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const AttnParams p) {
         int ldkv;
         if (sidx >= 0) {
             kg = p.k + (long long)sidx * p.Nk * p.ld_kv + head * D;
-            vg = p.v + (long long)sidx * p.Nk * p.ld_kv + head * D;
+            vg = p.v + (long long)sidx * p.Nk * p.ld_kv + head * p.vstride;
             ldkv = p.ld_kv;
         } else {
             const long long r2 = -(long long)(sidx + 1);
             kg = p.k2 + r2 * p.Nk * p.ld_kv2 + head * D;
-            vg = p.v2 + r2 * p.Nk * p.ld_kv2 + head * D;
+            vg = p.v2 + r2 * p.Nk * p.ld_kv2 + head * p.vstride;
             ldkv = p.ld_kv2;
         }
         auto load_kv = [&](int kt, int stage) {
@@ -268,7 +268,7 @@ int launch(const AttnParams& p, cudaStream_t st) {
 
 int gcb_attn_mma_launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2,
                         const void* v2, int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d,
-                        int n_src, const int32_t* src_index, const float* h_src_weight, float scale,
+                        int vstride, int n_src, const int32_t* src_index, const float* h_src_weight, float scale,
                         cudaStream_t stream) {
     AttnParams p;
     p.q = (const __half*)q;
@@ -285,6 +285,7 @@ int gcb_attn_mma_launch(const void* q, int ld_q, const void* k, const void* v, i
     p.Nq = Nq;
     p.Nk = Nk;
     p.heads = heads;
+    p.vstride = vstride;
     p.n_src_total = n_src;
     p.n_act = 0;
     for (int s = 0; s < n_src; ++s)
@@ -308,19 +309,21 @@ int gcb_attn_mma_launch(const void* q, int ld_q, const void* k, const void* v, i
 
 int gcb_attn_tc_supported(int Nq, int Nk, int heads, int d);
 int gcb_attn_tc_launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2, const void* v2,
-                       int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d, int n_src,
+                       int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d, int vstride, int n_src,
                        const int32_t* src_index, const float* h_src_weight, float scale, cudaStream_t stream);
 
 extern "C" int gcb_attn_multi_fwd(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2,
                                   const void* v2, int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads,
-                                  int d, int n_src, const int32_t* src_index, const float* h_src_weight, float scale,
-                                  int impl, void* stream) {
+                                  int d, int v_head_stride, int n_src, const int32_t* src_index,
+                                  const float* h_src_weight, float scale, int impl, void* stream) {
     GCB_CHECK_ARG(q && k && v && out && src_index && h_src_weight, "null pointer");
     GCB_CHECK_ARG(B > 0 && Nq > 0 && Nk > 0 && heads > 0 && heads < 65536 && B < 65536, "bad shape");
     GCB_CHECK_ARG(n_src >= 1 && n_src <= MAX_SRC, "n_src=%d out of range (1..%d)", n_src, MAX_SRC);
     GCB_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 2 == 0 && (k2 == nullptr || ld_kv2 % 8 == 0),
                   "row strides must keep 16-byte alignment");
     GCB_CHECK_ARG(d % 8 == 0, "head dim must be a multiple of 8");
+    GCB_CHECK_ARG(v_head_stride >= d && v_head_stride % 8 == 0, "v_head_stride=%d must be >= d and a multiple of 8",
+                  v_head_stride);
     if (const char* e = getenv("GCB_FORCE_ATTN_IMPL")) impl = atoi(e);
     if (impl == GCB_ATTN_AUTO) impl = gcb_attn_tc_supported(Nq, Nk, heads, d) ? GCB_ATTN_TCGEN05 : GCB_ATTN_MMA_SYNC;
     if (impl == GCB_ATTN_TCGEN05) {
@@ -328,10 +331,10 @@ extern "C" int gcb_attn_multi_fwd(const void* q, int ld_q, const void* k, const 
             gcb_set_error("tcgen05 attention does not support Nq=%d Nk=%d d=%d", Nq, Nk, d);
             return GCB_ERR_UNSUPPORTED;
         }
-        return gcb_attn_tc_launch(q, ld_q, k, v, ld_kv, k2, v2, ld_kv2, out, ld_out, B, Nq, Nk, heads, d, n_src,
-                                  src_index, h_src_weight, scale, (cudaStream_t)stream);
+        return gcb_attn_tc_launch(q, ld_q, k, v, ld_kv, k2, v2, ld_kv2, out, ld_out, B, Nq, Nk, heads, d, v_head_stride,
+                                  n_src, src_index, h_src_weight, scale, (cudaStream_t)stream);
     }
     GCB_CHECK_ARG(impl == GCB_ATTN_MMA_SYNC, "unknown attention impl %d", impl);
-    return gcb_attn_mma_launch(q, ld_q, k, v, ld_kv, k2, v2, ld_kv2, out, ld_out, B, Nq, Nk, heads, d, n_src, src_index,
-                               h_src_weight, scale, (cudaStream_t)stream);
+    return gcb_attn_mma_launch(q, ld_q, k, v, ld_kv, k2, v2, ld_kv2, out, ld_out, B, Nq, Nk, heads, d, v_head_stride, n_src,
+                               src_index, h_src_weight, scale, (cudaStream_t)stream);
 }

@@ -35,12 +35,17 @@ template <>
 struct Cfg<40> {
     static constexpr int D = 40, BN = 128, DK = 48, NV = 48, BOXES = 1;
     static constexpr bool ZERO_Q_PAD = true, ACC_IN_TMEM = false;
+    // exponentials per 8 evaluated by the FMA-pipe polynomial instead of the MUFU.  Measured on B200 (r1): 3/8 makes
+    // the kernel SLOWER (546 -> 485 TFLOP/s): 3-register FFMA/FADD issue at half rate per SM sub-partition, so the
+    // ~7-instruction polynomial costs more FMA-pipe time than the MUFU slot it frees.  Kept at 0.
+    static constexpr int POLY_OF_8 = 0;
     static constexpr uint32_t TM_S = 0, TM_O = 256, TM_O_STRIDE = 64, TM_P = 384, TM_ACC = 0;
 };
 template <>
 struct Cfg<80> {
     static constexpr int D = 80, BN = 64, DK = 80, NV = 80, BOXES = 2;
     static constexpr bool ZERO_Q_PAD = false, ACC_IN_TMEM = true;
+    static constexpr int POLY_OF_8 = 0;
     static constexpr uint32_t TM_S = 0, TM_O = 128, TM_O_STRIDE = 80, TM_P = 288, TM_ACC = 352;
 };
 
@@ -48,6 +53,8 @@ struct AttnTcParams {
     __half* out;
     int ld_out;
     int Nq, Nk, heads;
+    int vstride;      // elements between heads in a V row
+    int l_from_o;     // V column D holds 1.0: row sums come out of P V (column D of O)
     int n_src_total, n_act;
     int src_id[MAX_SRC];
     float weight[MAX_SRC];
@@ -74,6 +81,17 @@ __device__ __forceinline__ float ex2_f32(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// 2^x on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax, max rel. error 7.5e-5 - well below the fp16
+// rounding of P): used for a fraction of the elements so the MUFU (16 ex2/clk/SM) stops being the limiter at d=40.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.f);
+    const float fi = x + 12582912.f;  // 1.5 * 2^23: round(x) lands in the low mantissa bits
+    const float f = x - (fi - 12582912.f);  // [-0.5, 0.5]
+    float r = fmaf(f, 0.0551716648f, 0.2426111251f);
+    r = fmaf(r, f, 0.6932609677f);
+    r = fmaf(r, f, 0.9999280572f);
+    return __int_as_float(__float_as_int(r) + (__float_as_int(fi) << 23));
 }
 __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
     uint32_t y;
@@ -199,7 +217,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 mbar_expect_tx(fb, STAGE_BYTES);
 #pragma unroll
                 for (int bx = 0; bx < BOXES; ++bx)
-                    tma_load_2d(smem_u32(sm.v[st][bx]), second ? &tmV2 : &tmV, fb, head * D + bx * 64, row);
+                    tma_load_2d(smem_u32(sm.v[st][bx]), second ? &tmV2 : &tmV, fb, head * p.vstride + bx * 64, row);
             }
             __syncwarp();
         }
@@ -334,16 +352,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 // p = 2^(s*scale - m), kept in registers as packed halves (reusing the score registers) ...
                 const float negm = -m;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+                const bool sum_here = !p.l_from_o;
 #pragma unroll
                 for (int e = 0; e < BN / 2; e += 2) {
-                    const float p0 = ex2_f32(fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm));
-                    const float p1 = ex2_f32(fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm));
-                    const float p2 = ex2_f32(fmaf(__uint_as_float(sr[2 * e + 2]), p.scale_log2, negm));
-                    const float p3 = ex2_f32(fmaf(__uint_as_float(sr[2 * e + 3]), p.scale_log2, negm));
-                    l0 += p0;
-                    l1 += p1;
-                    l2 += p2;
-                    l3 += p3;
+                    const float x0 = fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm);
+                    const float x1 = fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm);
+                    const float x2 = fmaf(__uint_as_float(sr[2 * e + 2]), p.scale_log2, negm);
+                    const float x3 = fmaf(__uint_as_float(sr[2 * e + 3]), p.scale_log2, negm);
+                    // d=40 is exp-bound: POLY_OF_8 of every 8 exponentials run on the FMA pipes instead of the MUFU
+                    const float p0 = ex2_f32(x0);
+                    const float p1 = (C::POLY_OF_8 >= 4 || (C::POLY_OF_8 >= 2 && (e & 2))) ? ex2_poly(x1) : ex2_f32(x1);
+                    const float p2 = ex2_f32(x2);
+                    const float p3 = (C::POLY_OF_8 >= 3 || (C::POLY_OF_8 >= 1 && (e & 2))) ? ex2_poly(x3) : ex2_f32(x3);
+                    if (sum_here) {
+                        l0 += p0;
+                        l1 += p1;
+                        l2 += p2;
+                        l3 += p3;
+                    }
                     sr[e] = cvt_f16x2(p0, p1);
                     sr[e + 1] = cvt_f16x2(p2, p3);
                 }
@@ -364,6 +390,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int ilast = s * nkt + nkt - 1;
             mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)ilast) & 1u);
             tc_fence_after();
+            if (p.l_from_o) {
+                uint32_t lv[16];
+                tmem_ld_32x32b_x16(o_t + (uint32_t)(D / 16 * 16), lv);  // the 16-column chunk that holds column D
+                tc_wait_ld();
+                l = __uint_as_float(lv[D % 16]);
+            }
             const float wl = p.weight[s] / l;
 #pragma unroll
             for (int c = 0; c < C::NV / 16; ++c) {
@@ -429,8 +461,10 @@ int encode_rows(CUtensorMap* tm, const void* base, int ld, long long rows, int w
 
 template <int D_>
 int launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2, const void* v2, int ld_kv2,
-           int B, int Nq, int heads, const AttnTcParams& p, cudaStream_t stream) {
+           int B, int Nq, int heads, AttnTcParams& p, cudaStream_t stream) {
     using C = Cfg<D_>;
+    // ones column: only where the P V tile has spare columns (NV > D) and the caller laid V out with padded heads
+    p.l_from_o = (C::NV > C::D && p.vstride >= C::NV) ? 1 : 0;
     // tensor maps: inner extent = heads*d columns from each base pointer (columns beyond are zero-filled by TMA, so the
     // 64-wide boxes of the last head never read past their tensor).  The batch-row count of the K/V buffers is not
     // part of the ABI: rows are addressed through src_index, the row extent is left open.
@@ -440,10 +474,11 @@ int launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, con
     int rc;
     if ((rc = encode_rows(&tmQ, q, ld_q, (long long)B * Nq, width, BM))) return rc;
     if ((rc = encode_rows(&tmK, k, ld_kv, big, width, C::BN))) return rc;
-    if ((rc = encode_rows(&tmV, v, ld_kv, big, width, C::BN))) return rc;
+    const int vwidth = heads * p.vstride;
+    if ((rc = encode_rows(&tmV, v, ld_kv, big, vwidth, C::BN))) return rc;
     if (k2) {
         if ((rc = encode_rows(&tmK2, k2, ld_kv2, big, width, C::BN))) return rc;
-        if ((rc = encode_rows(&tmV2, v2, ld_kv2, big, width, C::BN))) return rc;
+        if ((rc = encode_rows(&tmV2, v2, ld_kv2, big, vwidth, C::BN))) return rc;
     } else {
         tmK2 = tmK;
         tmV2 = tmV;
@@ -471,7 +506,7 @@ int gcb_attn_tc_supported(int Nq, int Nk, int heads, int d) {
 }
 
 int gcb_attn_tc_launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2, const void* v2,
-                       int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d, int n_src,
+                       int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d, int vstride, int n_src,
                        const int32_t* src_index, const float* h_src_weight, float scale, cudaStream_t stream) {
     AttnTcParams p;
     memset(&p, 0, sizeof(p));
@@ -480,6 +515,7 @@ int gcb_attn_tc_launch(const void* q, int ld_q, const void* k, const void* v, in
     p.Nq = Nq;
     p.Nk = Nk;
     p.heads = heads;
+    p.vstride = vstride;
     p.n_src_total = n_src;
     for (int s = 0; s < n_src; ++s)
         if (h_src_weight[s] != 0.f) {

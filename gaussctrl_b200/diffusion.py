@@ -148,6 +148,24 @@ class PackedNet:
             self._cache[key] = (w.to(device=self.dev, dtype=torch.float16).contiguous(), b)
         return self._cache[key]
 
+    def qkv_ones_padded(self, attn: str, heads: int, pad_to: int):
+        """Fused [to_q | to_k | to_v] projection whose V block gives every head `pad_to` columns: the head's d value
+        columns, then a column that is identically 1.0 (zero weight row + bias 1), then zeros.  The tcgen05 attention
+        kernel reads the softmax row sums out of that ones column (gcb_attn_multi_fwd, v_head_stride)."""
+        key = f"qkvpad:{attn}:{pad_to}"
+        if key not in self._cache:
+            wq, wk, wv = (self.sd[f"{attn}.{n}.weight"] for n in ("to_q", "to_k", "to_v"))
+            C = wq.shape[0]
+            d = C // heads
+            wvp = torch.zeros((heads, pad_to, wv.shape[1]), dtype=wv.dtype)
+            wvp[:, :d] = wv.reshape(heads, d, -1)
+            w = torch.cat([wq, wk, wvp.reshape(heads * pad_to, -1)], dim=0)
+            b = torch.zeros((w.shape[0],), dtype=torch.float32)
+            b[2 * C + d::pad_to] = 1.0
+            self._cache[key] = (w.to(device=self.dev, dtype=torch.float16).contiguous(),
+                                b.to(device=self.dev, dtype=torch.float16))
+        return self._cache[key]
+
     def geglu(self, name: str):
         """GEGLU projection with rows interleaved per N tile for the fused epilogue."""
         key = "geglu:" + name
@@ -168,6 +186,7 @@ class SD15Denoiser:
         self.cnet = PackedNet(cnet_sd, self.dev, heads)
         self.heads = heads
         self.fuse_geglu = fuse_geglu
+        self.ones_column = False
         self.ch = [unet_sd[f"down_blocks.{i}.resnets.0.conv1.weight"].shape[0] for i in range(4)]
         self._temb_layout: Dict[int, Tuple[List[str], Dict[str, int], int]] = {}
         self.text_kv: Dict[Tuple[int, str, int], torch.Tensor] = {}
@@ -252,8 +271,16 @@ class SD15Denoiser:
         blk = p + ".transformer_blocks.0"
         # --- attn1: (cross-view) self-attention
         n1 = ops.layernorm(h, net.vec(blk + ".norm1.weight"), net.vec(blk + ".norm1.bias"))
-        wqkv, _ = net.cat_lin([blk + ".attn1.to_q", blk + ".attn1.to_k", blk + ".attn1.to_v"])
-        qkv = ops.linear(n1, wqkv)  # [B,N,3C]
+        if d == 40 and self.ones_column:
+            # head dim 40: V heads padded to 48 columns with a ones column -> row sums come out of the P V product
+            # (measured on B200: no gain over summing in the softmax threads - the kernel is MUFU-bound - so off by default)
+            wqkv, bqkv = net.qkv_ones_padded(blk + ".attn1", heads, 48)
+            qkv = ops.linear(n1, wqkv, bqkv)  # [B,N,2C+heads*48]
+            ld, vstride = 2 * C + heads * 48, 48
+        else:
+            wqkv, _ = net.cat_lin([blk + ".attn1.to_q", blk + ".attn1.to_k", blk + ".attn1.to_v"])
+            qkv = ops.linear(n1, wqkv)  # [B,N,3C]
+            ld, vstride = 3 * C, d
         layer = f"{net_id}:{blk}.attn1"
         if plan.gather is not None:
             # sharded reference pass (parallel.py): all-gather the rows' q|k|v so every reference row sees all references
@@ -265,8 +292,8 @@ class SD15Denoiser:
                 plan.record_kv[layer] = qkv
             kv2 = plan.ref_kv[layer] if plan.ref_kv is not None else None
         weights = plan.weights_unet if net_id == 0 else plan.weights_cnet
-        a = ops.attention(qkv, 0, 3 * C, qkv, C, 2 * C, 3 * C, kv2, C, 2 * C, 3 * C, B, N, N, heads, d, plan.src_index,
-                          weights)
+        a = ops.attention(qkv, 0, ld, qkv, C, 2 * C, ld, kv2, C, 2 * C, ld, B, N, N, heads, d, plan.src_index, weights,
+                          v_head_stride=vstride)
         wo, bo = net.lin(blk + ".attn1.to_out.0")
         h = ops.linear(a, wo, bo, residual=h)
         # --- attn2: text cross-attention (K/V precomputed by set_prompts)

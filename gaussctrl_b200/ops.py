@@ -146,7 +146,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 # ------------------------------------------------------------------------------------------------ attention
 def attention(q: torch.Tensor, q_off: int, ld_q: int, kv: torch.Tensor, k_off: int, v_off: int, ld_kv: int,
               kv2: Optional[torch.Tensor], k2_off: int, v2_off: int, ld_kv2: int, B: int, Nq: int, Nk: int, heads: int,
-              d: int, src_index: torch.Tensor, weights: Sequence[float], scale: Optional[float] = None) -> torch.Tensor:
+              d: int, src_index: torch.Tensor, weights: Sequence[float], scale: Optional[float] = None,
+              v_head_stride: Optional[int] = None) -> torch.Tensor:
     """Multi-source attention (see gcb_attn_multi_fwd).  q/k/v are given as (buffer, element offset, row stride) so
     they can be column slices of a fused QKV projection.  src_index: int32 [B, n_src] device tensor."""
     out = torch.empty((B, Nq, heads * d), dtype=torch.float16, device=q.device)
@@ -155,8 +156,9 @@ def attention(q: torch.Tensor, q_off: int, ld_q: int, kv: torch.Tensor, k_off: i
     w = (ctypes.c_float * n_src)(*[float(v) for v in weights])
     sc = d ** -0.5 if scale is None else scale
     check(lib.gcb_attn_multi_fwd(_p(q, q_off), ld_q, _p(kv, k_off), _p(kv, v_off), ld_kv, _p(kv2, k2_off),
-                                 _p(kv2, v2_off), ld_kv2, _p(out), heads * d, B, Nq, Nk, heads, d, n_src,
-                                 _p(src_index), w, sc, _ATTN_IMPL[0], _stream()))
+                                 _p(kv2, v2_off), ld_kv2, _p(out), heads * d, B, Nq, Nk, heads, d,
+                                 d if v_head_stride is None else v_head_stride, n_src, _p(src_index), w, sc,
+                                 _ATTN_IMPL[0], _stream()))
     LAUNCHES[0] += 1
     return out
 

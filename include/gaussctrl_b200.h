@@ -94,14 +94,17 @@ int gcb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* 
  * values < 0 index (k2,v2) at row -(value+1).  h_src_weight: host float[n_src]; zero-weight sources are skipped.
  * The reference's 5 passes are n_src=5, weights {c, (1-c)/4 x4}, src rows {b, ref0..ref3 of b's CFG half}
  * (utils.py:88-117); text cross-attention and the vanilla AttnProcessor are n_src=1.
- * ld_* are row strides in elements (>= heads*d) so q/k/v may be slices of a fused QKV projection. */
+ * ld_* are row strides in elements (>= heads*d) so q/k/v may be slices of a fused QKV projection.
+ * v_head_stride: elements between consecutive heads inside a V row (both V buffers).  Normally d.  If it is >= d+8,
+ * column d of every head must hold 1.0 (the caller's V projection writes it: zero weight rows + bias 1): the tcgen05
+ * kernel then gets the softmax row sums out of the P V product itself instead of adding them up in registers. */
 #define GCB_ATTN_AUTO 0     /* tcgen05 kernel where it is built for the shape, else the mma.sync kernel */
 #define GCB_ATTN_TCGEN05 1
 #define GCB_ATTN_MMA_SYNC 2
 int gcb_attn_multi_fwd(const void* q, int ld_q, const void* k, const void* v, int ld_kv, const void* k2,
                        const void* v2, int ld_kv2, void* out, int ld_out, int B, int Nq, int Nk, int heads, int d,
-                       int n_src, const int32_t* src_index, const float* h_src_weight, float scale, int impl,
-                       void* stream);
+                       int v_head_stride, int n_src, const int32_t* src_index, const float* h_src_weight, float scale,
+                       int impl, void* stream);
 
 /* Row softmax with scale, fp16 in/out, fp32 math (VAE mid-block attention, 1 head of dim 512). */
 int gcb_softmax_rows_fwd(const void* x, void* y, int rows, int cols, float scale, void* stream);

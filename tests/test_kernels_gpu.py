@@ -381,3 +381,32 @@ def test_tcgen05_attention(ops, case):
     want = cva.multi_source_attention(q, ksl, vsl, w, heads)
     rel, mx = _relerr(got.cpu(), want)
     assert rel < 3e-3, (rel, mx)
+
+
+def test_tcgen05_attention_ones_column(ops):
+    """d=40 with V heads padded to 48 columns and a ones column (row sums taken from the P V product) and the
+    polynomial exp2 offload: same result as the plain layout / the oracle."""
+    from oracle import crossview_attn as cva
+    B, N, heads, d = 4, 512, 8, 40
+    C = heads * d
+    F = B // 2
+    qkv = _rand((B, N, 3 * C), 21)
+    vpad = torch.zeros((B, N, heads, 48), dtype=torch.float16, device="cuda")
+    vpad[..., :d] = qkv[..., 2 * C:].reshape(B, N, heads, d)
+    vpad[..., d] = 1.0
+    qkvp = torch.cat([qkv[..., :2 * C], vpad.reshape(B, N, heads * 48)], dim=-1).contiguous()
+    ld = 2 * C + heads * 48
+    rows = [[h * F + f] + [h * F + r for r in (0, 1)] for h in range(2) for f in range(F)]
+    idx = torch.tensor(rows, dtype=torch.int32).cuda()
+    w = [0.6, 0.2, 0.2]
+    q, k, v = qkv.cpu()[..., :C], qkv.cpu()[..., C:2 * C], qkv.cpu()[..., 2 * C:]
+    ks, vs, ws = cva.crossview_sources(k, v, F, (0, 1), 0.6)
+    want = cva.multi_source_attention(q, ks, vs, ws, heads)
+    for impl in (1, 2):
+        ops.set_attn_impl(impl)
+        try:
+            got = ops.attention(qkvp, 0, ld, qkvp, C, 2 * C, ld, None, 0, 0, 0, B, N, N, heads, d, idx, w, v_head_stride=48)
+        finally:
+            ops.set_attn_impl(0)
+        rel, mx = _relerr(got.cpu(), want)
+        assert rel < 3e-3, (impl, rel, mx)

@@ -1,5 +1,5 @@
 """One denoising step of the hot path, eager (no CUDA graph), for ncu: the reference pass (R=4, CFG batch 8, K/V
-recorded) followed by one view batch (c=3, CFG batch 6, cached reference K/V) at 512^2 (64x64 latents)."""
+recorded) followed by one view batch (c=3, CFG batch 2*c, cached reference K/V) at 512^2 (64x64 latents)."""
 import os
 import sys
 
@@ -15,7 +15,7 @@ unet, cnet, _ = synthetic_weights(0, with_vae=False)
 den = SD15Denoiser(unet, cnet, "cuda")
 g = torch.Generator().manual_seed(0)
 den.set_prompts(torch.randn((2, 77, 768), generator=g))
-R, c = 4, 3
+R, c = 4, int(os.environ.get("GCB_PROFILE_VB", "12"))
 rec = {}
 ref_plan = literal_crossview_plan(R, "cuda", record_kv=rec)
 x_ref = torch.randn((2 * R, 64, 64, 4), generator=g).half().cuda()
