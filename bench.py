@@ -337,6 +337,9 @@ def main():
                                        "its 2R CFG rows with a per-layer NCCL all-gather of q|k|v"}}
         print(json.dumps(line))
     if world > 1:
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -200,7 +200,9 @@ class EditEngine:
         K/V; (2) the remaining views are denoised in batches of `view_batch`, reading that K/V.
         Reference views' own edited latents are rows of pass (1) (SURVEY §8a gotcha 6).
         `view_ids`: the subset of views this rank edits (multi-GPU sharding); default all.
-        `dist_ctx` = {"world", "rank", "gather": parallel.KVAllGather, "graph_refs": bool}: the reference pass is
+        `dist_ctx` = {"world", "rank", "gather": parallel.KVAllGather, "graph_refs": bool (default False: capturing the
+        NCCL all-gathers of the sharded reference pass in a CUDA graph deadlocked on the 2-GPU box, so that pass runs
+        eagerly; the view batches - 90 % of the work - are still graph replays)}: the reference pass is
         sharded over the ranks' CFG rows with a per-layer K/V all-gather; result rows of views this rank does not own
         stay zero (parallel.gather_view_results assembles them)."""
         assert guidance > 1.0
@@ -219,7 +221,7 @@ class EditEngine:
         if key not in self._steps:
             if world > 1:
                 rs = _ShardedRefStep(self.den, R, guidance, hw, world, dist_ctx["rank"], dist_ctx["gather"], ref_frames,
-                                     self.use_graphs and dist_ctx.get("graph_refs", True))
+                                     self.use_graphs and dist_ctx.get("graph_refs", False))
                 self._steps[key] = [rs, rs.rec, None]
             else:
                 rec0: Dict[str, torch.Tensor] = {}
