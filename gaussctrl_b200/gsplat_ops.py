@@ -31,8 +31,8 @@ def _host16(m: torch.Tensor):
     return (ctypes.c_float * 16)(*m.reshape(-1).tolist())
 
 
-def project_gaussians(means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, img_height, img_width,
-                      tile_bounds, clip_thresh: float = 0.01):
+def _project_gaussians_fwd(means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, img_height, img_width,
+                           tile_bounds, clip_thresh: float = 0.01):
     """-> (xys [N,2], depths [N], radii [N] i32, conics [N,3], num_tiles_hit [N] i32, cov3d [N,6])."""
     means3d, scales, quats = _f32(means3d), _f32(scales), _f32(quats)
     N, dev = means3d.shape[0], means3d.device
@@ -50,7 +50,7 @@ def project_gaussians(means3d, scales, glob_scale, quats, viewmat, projmat, fx, 
     return xys, depths, radii, conics, nth, cov3d
 
 
-def spherical_harmonics(degrees_to_use: int, viewdirs, coeffs):
+def _spherical_harmonics_fwd(degrees_to_use: int, viewdirs, coeffs):
     viewdirs, coeffs = _f32(viewdirs), _f32(coeffs)
     N, K = coeffs.shape[0], coeffs.shape[1]
     colors = torch.empty((N, 3), dtype=torch.float32, device=coeffs.device)
@@ -98,20 +98,108 @@ def rasterize_sorted(xys, conics, colors, opacity, gids, bins, img_height, img_w
     return out, fT, fidx
 
 
+class _ProjectGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, img_height, img_width,
+                tile_bounds, clip_thresh):
+        out = _project_gaussians_fwd(means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, img_height,
+                                     img_width, tile_bounds, clip_thresh)
+        xys, depths, radii, conics, nth, cov3d = out
+        ctx.save_for_backward(_f32(means3d), _f32(scales), _f32(quats), radii)
+        ctx.consts = (float(glob_scale), _host16(viewmat), _host16(projmat), float(fx), float(fy), float(cx), float(cy),
+                      int(img_height), int(img_width))
+        ctx.mark_non_differentiable(radii, nth, cov3d)
+        return out
+
+    @staticmethod
+    def backward(ctx, v_xys, v_depths, v_radii, v_conics, v_nth, v_cov3d):
+        means3d, scales, quats, radii = ctx.saved_tensors
+        gs, vm, pm, fx, fy, cx, cy, H, W = ctx.consts
+        N, dev = means3d.shape[0], means3d.device
+        z = lambda t, shp: torch.zeros(shp, dtype=torch.float32, device=dev) if t is None else _f32(t)  # noqa: E731
+        v_xys, v_depths, v_conics = z(v_xys, (N, 2)), z(v_depths, (N,)), z(v_conics, (N, 3))
+        v_means = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        v_scales = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        v_quats = torch.empty((N, 4), dtype=torch.float32, device=dev)
+        check(lib.gcb_project_gaussians_bwd(_p(means3d), _p(scales), gs, _p(quats), vm, pm, fx, fy, cx, cy, H, W,
+                                            _p(radii), _p(v_xys), _p(v_depths), _p(v_conics), N, _p(v_means),
+                                            _p(v_scales), _p(v_quats), _stream()))
+        ops.LAUNCHES[0] += 1
+        return (v_means, v_scales, None, v_quats) + (None,) * 10
+
+
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, degree, viewdirs, coeffs):
+        ctx.degree, ctx.K = int(degree), coeffs.shape[1]
+        ctx.save_for_backward(_f32(viewdirs))
+        return _spherical_harmonics_fwd(degree, viewdirs, coeffs)
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        (viewdirs,) = ctx.saved_tensors
+        N = viewdirs.shape[0]
+        v_coeffs = torch.empty((N, ctx.K, 3), dtype=torch.float32, device=viewdirs.device)
+        check(lib.gcb_sh_bwd(ctx.degree, ctx.K, _p(viewdirs), _p(_f32(v_colors)), _p(v_coeffs), N, _stream()))
+        ops.LAUNCHES[0] += 1
+        return None, None, v_coeffs  # view directions come from detached means (gc_model.py:163)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width, background):
+        H, W = int(img_height), int(img_width)
+        tile_bounds = ((W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK, 1)
+        gids, bins, _, M = bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds)
+        img, fT, fidx = rasterize_sorted(xys, conics, colors, opacity, gids, bins, H, W, background)
+        ctx.save_for_backward(_f32(xys), _f32(conics), _f32(colors), _f32(opacity).reshape(-1), gids, bins, fT, fidx,
+                              background.detach().to("cpu", torch.float32))
+        ctx.size = (H, W)
+        return img, 1.0 - fT
+
+    @staticmethod
+    def backward(ctx, v_img, v_alpha):
+        xys, conics, colors, opac, gids, bins, fT, fidx, bg = ctx.saved_tensors
+        H, W = ctx.size
+        N, C, dev = xys.shape[0], colors.shape[1], xys.device
+        v_xy = torch.zeros((N, 2), dtype=torch.float32, device=dev)
+        v_conic = torch.zeros((N, 3), dtype=torch.float32, device=dev)
+        v_colors = torch.zeros((N, C), dtype=torch.float32, device=dev)
+        v_opac = torch.zeros((N,), dtype=torch.float32, device=dev)
+        bgc = (ctypes.c_float * C)(*[float(v) for v in bg.reshape(-1).tolist()])
+        check(lib.gcb_rasterize_bwd(_p(xys), _p(conics), _p(colors), _p(opac), _p(gids), _p(bins), H, W, C, bgc, _p(fT),
+                                    _p(fidx), _p(_f32(v_img)), _p(None if v_alpha is None else _f32(v_alpha)), _p(v_xy),
+                                    _p(v_conic), _p(v_colors), _p(v_opac), _stream()))
+        ops.LAUNCHES[0] += 1
+        return v_xy, None, None, v_conic, None, v_colors, v_opac[:, None], None, None, None
+
+
+def project_gaussians(means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, img_height, img_width,
+                      tile_bounds, clip_thresh: float = 0.01):
+    """gsplat 0.1.3 `project_gaussians` (differentiable w.r.t. means3d, scales, quats)."""
+    return _ProjectGaussians.apply(means3d, scales, glob_scale, quats, viewmat, projmat, fx, fy, cx, cy, img_height,
+                                   img_width, tile_bounds, clip_thresh)
+
+
+def spherical_harmonics(degrees_to_use: int, viewdirs, coeffs):
+    """gsplat 0.1.3 `spherical_harmonics` (differentiable w.r.t. coeffs)."""
+    return _SphericalHarmonics.apply(degrees_to_use, viewdirs, coeffs)
+
+
 def rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width,
                         background: Optional[torch.Tensor] = None, return_alpha: bool = False):
-    """gsplat 0.1.3 signature (forward).  colors [N,C], C in {1,3,4}."""
+    """gsplat 0.1.3 signature; differentiable w.r.t. xys, conics, colors, opacity.  colors [N,C], C in {1,3,4}."""
     C = colors.shape[-1]
     dev = colors.device
     if background is None:
         background = torch.ones(C, dtype=torch.float32, device=dev)
-    tile_bounds = ((img_width + BLOCK - 1) // BLOCK, (img_height + BLOCK - 1) // BLOCK, 1)
-    gids, bins, _, M = bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds)
-    if M < 1:
+    if int(num_tiles_hit.sum().item()) < 1:
         img = torch.ones(img_height, img_width, C, device=dev) * background.to(dev)
         return (img, torch.zeros(img_height, img_width, device=dev)) if return_alpha else img
-    img, fT, _ = rasterize_sorted(xys, conics, colors, opacity, gids, bins, img_height, img_width, background)
-    return (img, 1.0 - fT) if return_alpha else img
+    opacity = opacity if opacity.dim() == 2 else opacity[:, None]
+    img, alpha = _RasterizeGaussians.apply(xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height,
+                                           img_width, background)
+    return (img, alpha) if return_alpha else img
 
 
 def rasterize_rgbd(xys, depths, radii, conics, num_tiles_hit, rgbs, opacity, img_height, img_width, background):

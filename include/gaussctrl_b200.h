@@ -182,6 +182,29 @@ int gcb_rasterize_fwd(const float* xys, const float* conics, const float* colors
                       const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
                       const float* h_background, float* out_img, float* final_T, int32_t* final_idx, void* stream);
 
+/* ---- backward (the 3DGS fine-tune step after the edit: gc_trainer.py:257-301 -> loss.backward() through gsplat's
+ *      autograd Functions).  Exact derivatives of the forward kernels above. ---- */
+
+/* gsplat rasterize_backward: v_out [H,W,C] and optional v_out_alpha [H,W] (NULL = no alpha gradient) ->
+ * v_xy [N,2], v_conic [N,3], v_colors [N,C], v_opacity [N]; the caller zero-initialises them (accumulated with one
+ * atomicAdd per warp and Gaussian).  v_conic is the true gradient w.r.t. the stored conic (a, b, c). */
+int gcb_rasterize_bwd(const float* xys, const float* conics, const float* colors, const float* opacities,
+                      const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
+                      const float* h_background, const float* final_T, const int32_t* final_idx, const float* v_out,
+                      const float* v_out_alpha, float* v_xy, float* v_conic, float* v_colors, float* v_opacity,
+                      void* stream);
+
+/* gsplat project_gaussians backward: (v_xy, v_depth, v_conic) -> v_means3d [N,3], v_scales [N,3], v_quats [N,4]
+ * (zero for Gaussians with radii == 0). */
+int gcb_project_gaussians_bwd(const float* means3d, const float* scales, float glob_scale, const float* quats,
+                              const float* h_viewmat, const float* h_projmat, float fx, float fy, float cx, float cy,
+                              int img_h, int img_w, const int32_t* radii, const float* v_xy, const float* v_depth,
+                              const float* v_conic, int N, float* v_means3d, float* v_scales, float* v_quats,
+                              void* stream);
+
+/* spherical_harmonics backward: v_coeffs [N,K,3] = basis_k(viewdir) * v_colors (zero beyond the active degree). */
+int gcb_sh_bwd(int degree, int K, const float* viewdirs, const float* v_colors, float* v_coeffs, int N, void* stream);
+
 /* get_outputs epilogue (gc_model.py:188,203-204): rgb = min(rgb,1); depth = depth/alpha where alpha>0 else 1000.
  * in: img4 [H,W,4] (r,g,b,depth-accum), final_T [H,W]; out: rgb [H,W,3], depth [H,W,1], alpha [H,W,1]. */
 int gcb_raster_finalize(const float* img4, const float* final_T, float* rgb, float* depth, float* alpha, int HW,

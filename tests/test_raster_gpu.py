@@ -140,3 +140,31 @@ def test_get_outputs_fused_rgbd():
     solid = want["accumulation"] > 1e-3
     assert ((d_g - d_w).abs() / d_w.abs().clamp(min=1e-3))[solid].max().item() < 1e-3
     assert torch.equal(d_g[want["accumulation"] == 0], d_w[want["accumulation"] == 0])  # 1000 where nothing was hit
+
+
+def test_backward_matches_oracle_autograd():
+    """Training-mode render + backward (the 3DGS fine-tune step) through the gsplat-seam autograd
+    Functions vs autograd of the oracle restatement, for every Gaussian parameter group."""
+    from oracle import gsplat_ref as gr
+    from gaussctrl_b200.gc_model import render_gaussians
+    N, H, W = 1200, 48, 48
+    P = _scene(N, seed=21)
+    c2w, fx, fy, cx, cy = _camera(H, W)
+    bg = torch.tensor([0.3, 0.1, 0.6])
+    g = torch.Generator().manual_seed(5)
+    G_rgb, G_a = torch.randn((H, W, 3), generator=g), torch.randn((H, W, 1), generator=g)
+
+    def run(params, render, dev):
+        leaves = {k: v.clone().to(dev).requires_grad_(True) for k, v in params.items()}
+        out = render(leaves)
+        loss = (out["rgb"] * G_rgb.to(dev)).sum() + (out["accumulation"] * G_a.to(dev)).sum()
+        loss.backward()
+        return {k: v.grad.detach().cpu() for k, v in leaves.items()}, out
+
+    want, _ = run(P, lambda p: gr.get_outputs(p, c2w, fx, fy, cx, cy, H, W, 3, bg, training=True), "cpu")
+    got, out = run(P, lambda p: render_gaussians(p, c2w, fx, fy, cx, cy, H, W, 3, bg.cuda(), training=True), "cuda")
+    assert out["depth"] is None  # training mode renders no depth (gc_model.py:190)
+    for k in want:
+        rel = ((got[k] - want[k]).norm() / (want[k].norm() + 1e-12)).item()
+        # fp32 with atomics (summation order) and different exp implementations
+        assert rel < 2e-3, (k, rel)
