@@ -207,6 +207,10 @@ def main():
         dm.train_data[i]["depth_image"] = out["depth"].permute(2, 0, 1).cpu().to(torch.float32).numpy()
         dm.train_data[i]["z_0_image"] = torch.randn((1, 4, HW_LAT, HW_LAT), generator=g).numpy()
     raster_ms = sorted(raster_ms[1:]) if len(raster_ms) > 1 else raster_ms
+    from gaussctrl_b200 import gsplat_ops as _go
+    n_isect = int(_go.LAST_M[0])
+    # algorithmic bytes of one eval render: 244 N + 48 N_v + 152 M + 5.2 MB, N_v <= N
+    raster_bytes = 244.0 * args.gaussians + 48.0 * args.gaussians + 152.0 * n_isect + 5.2e6
 
     # ---- device-resident inputs for `value`
     z_dev = torch.from_numpy(np.concatenate([d["z_0_image"] for d in dm.train_data])).to(dev, torch.float16)
@@ -330,6 +334,11 @@ def main():
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "extra": {"raster_ms_per_view_median": raster_ms[len(raster_ms) // 2] if raster_ms else None,
+                          "raster": {"intersections": n_isect, "algorithmic_bytes": raster_bytes,
+                                     "achieved_gbs": raster_bytes / (raster_ms[len(raster_ms) // 2] / 1e3) / 1e9
+                                     if raster_ms else None,
+                                     "note": "CUDA events around GaussCtrlModel.get_outputs_for_camera (host syncs of "
+                                             "the binning included); roofline bound = HBM"},
                           "schedule": "refs_once (reference views denoised once per DDIM step, K/V recorded)",
                           "view_batch": args.view_batch, "breakdown": breakdown,
                           "views_total": V,

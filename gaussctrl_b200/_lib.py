@@ -49,6 +49,8 @@ SIGNATURES = {
     "gcb_depth_to_disparity": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "gcb_project_gaussians_fwd": (c_int, [_P, _P, c_float, _P, _FP, _FP, c_float, c_float, c_float, c_float, c_int,
                                           c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gcb_project_sh_fused_fwd": (c_int, [_P] * 6 + [_FP, _FP, _FP, c_float, c_float, c_float, c_float] + [c_int] * 6 +
+                                 [_P] * 7 + [_P]),
     "gcb_sh_fwd": (c_int, [c_int, c_int, _P, _P, _P, c_int, _P]),
     "gcb_scan_workspace_bytes": (c_size_t, [c_int]),
     "gcb_cumsum_i32": (c_int, [_P, _P, c_int, _P, c_size_t, _P]),

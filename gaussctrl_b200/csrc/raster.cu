@@ -3,7 +3,7 @@
 // :174-186 and :191-202 (rasterize_gaussians).  fp32 SIMT, HBM/L2-bound.
 //
 // Binning is NOT gsplat's "sort M 64-bit (tile|depth) keys": the Gaussians (N) are ordered by depth once
-// (4 stable 8-bit radix passes over N 32-bit keys), intersections (M ~ 10 N) are emitted in that order and
+// (3 stable radix passes of 11+11+10 bits over N 32-bit keys), intersections (M ~ 10 N) are emitted in that order and
 // ONE stable 10-bit radix pass by tile id groups them.  The result is identical to a stable sort by
 // (tile << 32 | depth bits) with ties by Gaussian id - the order the oracle defines - at a fraction of the traffic.
 //
@@ -44,21 +44,18 @@ __device__ __forceinline__ void tile_bbox(float x, float y, float radius, int tb
     y1 = clampi(f2i_sat(add(add(tcy, tr), 1.0f)), 0, tby);
 }
 
-__global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ means, const float* __restrict__ scales,
-                                                      const float* __restrict__ quats, const ProjConst P, int N,
-                                                      float* __restrict__ xys, float* __restrict__ depths,
-                                                      int32_t* __restrict__ radii, float* __restrict__ conics,
-                                                      int32_t* __restrict__ nth, float* __restrict__ cov3d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const float px = means[3 * i], py = means[3 * i + 1], pz = means[3 * i + 2];
+// projection of one Gaussian (gsplat project_gaussians_forward_kernel), shared by the seam kernel and the fused one
+__device__ __forceinline__ void project_one(const ProjConst& P, int i, float px, float py, float pz, float s0, float s1,
+                                            float s2, float w, float x, float y, float z, float* __restrict__ xys,
+                                            float* __restrict__ depths, int32_t* __restrict__ radii,
+                                            float* __restrict__ conics, int32_t* __restrict__ nth,
+                                            float* __restrict__ cov3d) {
     const float* vm = P.vm;
     const float tx = add(dot3(vm[0], px, vm[1], py, vm[2], pz), vm[3]);
     const float ty = add(dot3(vm[4], px, vm[5], py, vm[6], pz), vm[7]);
     const float tz = add(dot3(vm[8], px, vm[9], py, vm[10], pz), vm[11]);
     bool valid = tz > P.clip;
 
-    float w = quats[4 * i], x = quats[4 * i + 1], y = quats[4 * i + 2], z = quats[4 * i + 3];
     const float inv = rcp(__fsqrt_rn(add(add(add(mul(w, w), mul(x, x)), mul(y, y)), mul(z, z))));
     w = mul(w, inv);
     x = mul(x, inv);
@@ -73,8 +70,7 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
     const float r20 = mul(2.0f, sub(mul(x, z), mul(w, y)));
     const float r21 = mul(2.0f, add(mul(y, z), mul(w, x)));
     const float r22 = sub(1.0f, mul(2.0f, add(mul(x, x), mul(y, y))));
-    const float sx = mul(P.glob_scale, scales[3 * i]), sy = mul(P.glob_scale, scales[3 * i + 1]),
-                sz = mul(P.glob_scale, scales[3 * i + 2]);
+    const float sx = mul(P.glob_scale, s0), sy = mul(P.glob_scale, s1), sz = mul(P.glob_scale, s2);
     const float m00 = mul(r00, sx), m01 = mul(r01, sy), m02 = mul(r02, sz);
     const float m10 = mul(r10, sx), m11 = mul(r11, sy), m12 = mul(r12, sz);
     const float m20 = mul(r20, sx), m21 = mul(r21, sy), m22 = mul(r22, sz);
@@ -146,6 +142,17 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
     nth[i] = valid ? area : 0;
 }
 
+__global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ means, const float* __restrict__ scales,
+                                                      const float* __restrict__ quats, const ProjConst P, int N,
+                                                      float* __restrict__ xys, float* __restrict__ depths,
+                                                      int32_t* __restrict__ radii, float* __restrict__ conics,
+                                                      int32_t* __restrict__ nth, float* __restrict__ cov3d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    project_one(P, i, means[3 * i], means[3 * i + 1], means[3 * i + 2], scales[3 * i], scales[3 * i + 1], scales[3 * i + 2],
+                quats[4 * i], quats[4 * i + 1], quats[4 * i + 2], quats[4 * i + 3], xys, depths, radii, conics, nth, cov3d);
+}
+
 // ------------------------------------------------------------------------------------------ spherical harmonics
 __constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
                                0.5462742152960396f};
@@ -205,6 +212,63 @@ __global__ void __launch_bounds__(256) sh_fwd_kernel(int degree, int K, const fl
         colors[3 * gi + 1] = g;
         colors[3 * gi + 2] = b;
     }
+}
+
+// Fused eval-path front end of GaussCtrlModel.get_outputs (gc_model.py:138-167): ONE pass over the 236 B/Gaussian
+// parameter record does exp(scales), quaternion normalisation, projection, view direction, SH colour (+0.5, clamp >= 0)
+// and sigmoid(opacity).  A warp stages its 32 Gaussians' 45 SH-rest floats through shared memory (coalesced reads).
+// Also writes (r, g, b, depth) as the 4-channel colour of the fused rgb+depth composite.
+__global__ void __launch_bounds__(256) project_sh_fused_kernel(
+    const float* __restrict__ means, const float* __restrict__ log_scales, const float* __restrict__ quats,
+    const float* __restrict__ fdc, const float* __restrict__ frest, const float* __restrict__ opac_logit,
+    const ProjConst P, float ox, float oy, float oz, int degree, int N, float* __restrict__ xys,
+    float* __restrict__ depths, int32_t* __restrict__ radii, float* __restrict__ conics, int32_t* __restrict__ nth,
+    float* __restrict__ rgbd, float* __restrict__ opac) {
+    __shared__ float s_rest[8][32 * 45 + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long g0 = ((long long)blockIdx.x * 8 + warp) * 32;
+    if (g0 >= N) return;
+    const int cnt = (int)min(32ll, N - g0);
+    if (degree > 0) {
+        const float* src = frest + g0 * 45;
+        for (int i = lane; i < cnt * 45; i += 32) s_rest[warp][i] = src[i];
+    }
+    __syncwarp();
+    if (lane >= cnt) return;
+    const int i = (int)(g0 + lane);
+    const float px = means[3 * i], py = means[3 * i + 1], pz = means[3 * i + 2];
+    // quats / quats.norm() as the reference does before calling project_gaussians (gc_model.py:144)
+    float qw = quats[4 * i], qx = quats[4 * i + 1], qy = quats[4 * i + 2], qz = quats[4 * i + 3];
+    const float qn = __fsqrt_rn(add(add(add(mul(qw, qw), mul(qx, qx)), mul(qy, qy)), mul(qz, qz)));
+    qw = __fdiv_rn(qw, qn);
+    qx = __fdiv_rn(qx, qn);
+    qy = __fdiv_rn(qy, qn);
+    qz = __fdiv_rn(qz, qn);
+    project_one(P, i, px, py, pz, expf(log_scales[3 * i]), expf(log_scales[3 * i + 1]), expf(log_scales[3 * i + 2]), qw,
+                qx, qy, qz, xys, depths, radii, conics, nth, nullptr);
+    // view direction from the camera origin, SH colour
+    float dx = px - ox, dy = py - oy, dz = pz - oz;
+    const float dn = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx /= dn;
+    dy /= dn;
+    dz /= dn;
+    float bas[16];
+    sh_basis(degree, dx, dy, dz, bas);
+    float r = bas[0] * fdc[3 * i], g = bas[0] * fdc[3 * i + 1], b = bas[0] * fdc[3 * i + 2];
+    const int nb = (degree + 1) * (degree + 1);
+    const float* c = &s_rest[warp][lane * 45];
+    for (int k = 1; k < nb; ++k) {
+        r += bas[k] * c[3 * (k - 1)];
+        g += bas[k] * c[3 * (k - 1) + 1];
+        b += bas[k] * c[3 * (k - 1) + 2];
+    }
+    float4 o;
+    o.x = fmaxf(r + 0.5f, 0.f);
+    o.y = fmaxf(g + 0.5f, 0.f);
+    o.z = fmaxf(b + 0.5f, 0.f);
+    o.w = depths[i];
+    reinterpret_cast<float4*>(rgbd)[i] = o;
+    opac[i] = 1.f / (1.f + expf(-opac_logit[i]));
 }
 
 // ------------------------------------------------------------------------------------------ scan (int32)
@@ -313,49 +377,62 @@ int scan_i32(const int* in, int* out, long long n, int inclusive, int* ws, cudaS
 }
 
 // ------------------------------------------------------------------------------------------ stable radix pass
-constexpr int RP_WARPS = 8, RP_PER_WARP = 1024, RP_PER_BLOCK = RP_WARPS * RP_PER_WARP, RP_MAX_BINS = 1024;
-
-__device__ __forceinline__ void rp_count(const uint32_t* __restrict__ keys, long long n, int shift, uint32_t mask,
-                                         int* cnt_w) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long w0 = (long long)blockIdx.x * RP_PER_BLOCK + (long long)warp * RP_PER_WARP;
-    for (int it = 0; it < RP_PER_WARP / 32; ++it) {
-        const long long i = w0 + it * 32 + lane;
-        const bool act = i < n;
-        const unsigned am = __ballot_sync(0xffffffffu, act);
-        if (act) {
-            const uint32_t bin = (keys[i] >> shift) & mask;
-            const unsigned peers = __match_any_sync(am, bin);
-            if ((peers & ((1u << lane) - 1)) == 0) cnt_w[bin] += __popc(peers);
-        }
-        __syncwarp();
-    }
-}
+// Block = 8 warps x 8 batches x 32 keys = 2048 keys.  Histogram kernel: shared-memory atomics (order irrelevant).
+// Scatter kernel: ONE traversal - keys stay in registers, each key records (same-digit keys seen earlier by its warp)
+// + (rank among equal digits inside its 32-key batch, __match_any_sync); after the block-wide exclusive bases are
+// known the final position is base[warp][digit] + local rank.  Stable by construction (block, warp, batch, lane).
+constexpr int RP_WARPS = 8, RP_BATCHES = 8, RP_PER_WARP = RP_BATCHES * 32, RP_PER_BLOCK = RP_WARPS * RP_PER_WARP;
+constexpr int RP_MAX_BINS = 2048;
 
 __global__ void __launch_bounds__(256) rp_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift,
                                                       int bins, int* __restrict__ counts) {
-    extern __shared__ int s_cnt[];  // [RP_WARPS][bins]
-    for (int i = threadIdx.x; i < RP_WARPS * bins; i += 256) s_cnt[i] = 0;
+    extern __shared__ int s_cnt[];  // [bins]
+    for (int i = threadIdx.x; i < bins; i += 256) s_cnt[i] = 0;
     __syncthreads();
-    rp_count(keys, n, shift, (uint32_t)bins - 1, s_cnt + (threadIdx.x >> 5) * bins);
-    __syncthreads();
-    for (int b = threadIdx.x; b < bins; b += 256) {
-        int t = 0;
+    const uint32_t mask = (uint32_t)bins - 1;
+    const long long b0 = (long long)blockIdx.x * RP_PER_BLOCK;
 #pragma unroll
-        for (int w = 0; w < RP_WARPS; ++w) t += s_cnt[w * bins + b];
-        counts[(long long)b * gridDim.x + blockIdx.x] = t;
+    for (int it = 0; it < RP_PER_BLOCK / 256; ++it) {
+        const long long i = b0 + it * 256 + threadIdx.x;
+        if (i < n) atomicAdd(&s_cnt[(keys[i] >> shift) & mask], 1);
     }
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += 256) counts[(long long)b * gridDim.x + blockIdx.x] = s_cnt[b];
 }
 
 __global__ void __launch_bounds__(256) rp_scatter_kernel(const uint32_t* __restrict__ keys,
                                                          const int32_t* __restrict__ vals, long long n, int shift,
                                                          int bins, const int* __restrict__ offsets,
                                                          uint32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
-    extern __shared__ int s_cnt[];  // [RP_WARPS][bins] -> running write positions
+    extern __shared__ int s_cnt[];  // [RP_WARPS][bins]: per-warp digit counts, then running write bases
     for (int i = threadIdx.x; i < RP_WARPS * bins; i += 256) s_cnt[i] = 0;
     __syncthreads();
     const uint32_t mask = (uint32_t)bins - 1;
-    rp_count(keys, n, shift, mask, s_cnt + (threadIdx.x >> 5) * bins);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* cnt_w = s_cnt + warp * bins;
+    const long long w0 = (long long)blockIdx.x * RP_PER_BLOCK + (long long)warp * RP_PER_WARP;
+    uint32_t key[RP_BATCHES];
+    int32_t val[RP_BATCHES];
+    int lrank[RP_BATCHES];
+#pragma unroll
+    for (int it = 0; it < RP_BATCHES; ++it) {
+        const long long i = w0 + it * 32 + lane;
+        const bool act = i < n;
+        const unsigned am = __ballot_sync(0xffffffffu, act);
+        lrank[it] = -1;
+        if (act) {
+            key[it] = keys[i];
+            val[it] = vals ? vals[i] : (int32_t)i;
+            const uint32_t bin = (key[it] >> shift) & mask;
+            const unsigned peers = __match_any_sync(am, bin);
+            const int rank = __popc(peers & ((1u << lane) - 1));
+            const int prior = cnt_w[bin];
+            __syncwarp(am);
+            if (rank == 0) cnt_w[bin] = prior + __popc(peers);
+            lrank[it] = prior + rank;
+        }
+        __syncwarp();
+    }
     __syncthreads();
     for (int b = threadIdx.x; b < bins; b += 256) {
         int run = offsets[(long long)b * gridDim.x + blockIdx.x];
@@ -367,25 +444,13 @@ __global__ void __launch_bounds__(256) rp_scatter_kernel(const uint32_t* __restr
         }
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* pos_w = s_cnt + warp * bins;
-    const long long w0 = (long long)blockIdx.x * RP_PER_BLOCK + (long long)warp * RP_PER_WARP;
-    for (int it = 0; it < RP_PER_WARP / 32; ++it) {
-        const long long i = w0 + it * 32 + lane;
-        const bool act = i < n;
-        const unsigned am = __ballot_sync(0xffffffffu, act);
-        if (act) {
-            const uint32_t key = keys[i];
-            const uint32_t bin = (key >> shift) & mask;
-            const unsigned peers = __match_any_sync(am, bin);
-            const int rank = __popc(peers & ((1u << lane) - 1));
-            const int pos = pos_w[bin] + rank;
-            __syncwarp(am);
-            if (rank == 0) pos_w[bin] += __popc(peers);
-            if (keys_out) keys_out[pos] = key;
-            vals_out[pos] = vals ? vals[i] : (int32_t)i;
+#pragma unroll
+    for (int it = 0; it < RP_BATCHES; ++it) {
+        if (lrank[it] >= 0) {
+            const int pos = cnt_w[(key[it] >> shift) & mask] + lrank[it];
+            if (keys_out) keys_out[pos] = key[it];
+            vals_out[pos] = val[it];
         }
-        __syncwarp();
     }
 }
 
@@ -397,9 +462,15 @@ int radix_pass(const uint32_t* keys, const int32_t* vals, long long n, int shift
     const int bins = 1 << bits;
     const long long nb = rp_blocks(n);
     const size_t smem = (size_t)RP_WARPS * bins * sizeof(int);
+    static bool configured = false;
+    if (!configured) {
+        GCB_CUDA(cudaFuncSetAttribute(rp_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      RP_WARPS * RP_MAX_BINS * (int)sizeof(int)));
+        configured = true;
+    }
     int* counts = ws;
     int* scan_ws = ws + (long long)bins * nb;
-    rp_hist_kernel<<<(unsigned)nb, 256, smem, st>>>(keys, n, shift, bins, counts);
+    rp_hist_kernel<<<(unsigned)nb, 256, (size_t)bins * sizeof(int), st>>>(keys, n, shift, bins, counts);
     int rc = scan_i32(counts, counts, (long long)bins * nb, 0, scan_ws, st);
     if (rc != GCB_OK) return rc;
     rp_scatter_kernel<<<(unsigned)nb, 256, smem, st>>>(keys, vals, n, shift, bins, counts, keys_out, vals_out);
@@ -572,6 +643,46 @@ extern "C" int gcb_project_gaussians_fwd(const float* means3d, const float* scal
     return GCB_OK;
 }
 
+static void fill_proj_const(ProjConst& P, const float* h_viewmat, const float* h_projmat, float fx, float fy, float cx,
+                            float cy, int img_h, int img_w, int tile_bx, int tile_by, float clip_thresh, float glob_scale) {
+    for (int i = 0; i < 12; ++i) P.vm[i] = h_viewmat[i];
+    for (int i = 0; i < 16; ++i) P.pm[i] = h_projmat[i];
+    P.fx = fx;
+    P.fy = fy;
+    P.cx = cx;
+    P.cy = cy;
+    P.lim_x = 1.3f * (float)(0.5 * (double)img_w / (double)fx);
+    P.lim_y = 1.3f * (float)(0.5 * (double)img_h / (double)fy);
+    P.clip = clip_thresh;
+    P.glob_scale = glob_scale;
+    P.half_w = 0.5f * (float)img_w;
+    P.half_h = 0.5f * (float)img_h;
+    P.tbx = tile_bx;
+    P.tby = tile_by;
+}
+
+extern "C" int gcb_project_sh_fused_fwd(const float* means3d, const float* log_scales, const float* quats,
+                                        const float* features_dc, const float* features_rest,
+                                        const float* opacity_logits, const float* h_viewmat, const float* h_projmat,
+                                        const float* h_cam_origin, float fx, float fy, float cx, float cy, int img_h,
+                                        int img_w, int tile_bx, int tile_by, int sh_degree, int N, float* xys,
+                                        float* depths, int32_t* radii, float* conics, int32_t* num_tiles_hit,
+                                        float* rgbd, float* opac, void* stream) {
+    GCB_CHECK_ARG(means3d && log_scales && quats && features_dc && opacity_logits && h_viewmat && h_projmat && h_cam_origin,
+                  "null input");
+    GCB_CHECK_ARG(sh_degree >= 0 && sh_degree <= 3 && (sh_degree == 0 || features_rest), "bad SH degree / features_rest");
+    GCB_CHECK_ARG(xys && depths && radii && conics && num_tiles_hit && rgbd && opac, "null output");
+    if (N == 0) return GCB_OK;
+    ProjConst P;
+    fill_proj_const(P, h_viewmat, h_projmat, fx, fy, cx, cy, img_h, img_w, tile_bx, tile_by, 0.01f, 1.0f);
+    project_sh_fused_kernel<<<gcb_cdiv(N, 256), 256, 0, ST>>>(means3d, log_scales, quats, features_dc, features_rest,
+                                                              opacity_logits, P, h_cam_origin[0], h_cam_origin[1],
+                                                              h_cam_origin[2], sh_degree, N, xys, depths, radii, conics,
+                                                              num_tiles_hit, rgbd, opac);
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
 extern "C" int gcb_sh_fwd(int degree, int K, const float* viewdirs, const float* coeffs, float* colors, int N,
                           void* stream) {
     GCB_CHECK_ARG(viewdirs && coeffs && colors, "null pointer");
@@ -603,7 +714,7 @@ extern "C" int gcb_cumsum_i32(const int32_t* in, int32_t* out, int N, void* work
 
 // workspace layout of gcb_depth_order: keys A/B [N] u32, ids B [N] i32, nth_sorted [N] i32, radix/scan scratch
 extern "C" size_t gcb_depth_order_workspace_bytes(int N) {
-    return ((size_t)4 * N + radix_ws_ints(N, 8) + scan_ws_ints(N) + 64) * sizeof(int);
+    return ((size_t)4 * N + radix_ws_ints(N, 11) + scan_ws_ints(N) + 64) * sizeof(int);
 }
 
 extern "C" int gcb_depth_order(const float* depths, const int32_t* num_tiles_hit, int N, int32_t* sorted_ids,
@@ -619,13 +730,12 @@ extern "C" int gcb_depth_order(const float* depths, const int32_t* num_tiles_hit
     int32_t* vB = (int32_t*)(kB + N);
     int32_t* nth_sorted = vB + N;
     int* scratch = (int*)(nth_sorted + N);
-    // depths are >= 0 so their bit patterns order like unsigned integers; 4 stable LSD passes of 8 bits
+    // depths are >= 0 so their bit patterns order like unsigned integers; 3 stable LSD passes of 11 + 11 + 10 bits
     const uint32_t* dk = reinterpret_cast<const uint32_t*>(depths);
     int rc;
-    if ((rc = radix_pass(dk, nullptr, N, 0, 8, kA, sorted_ids, scratch, ST))) return rc;
-    if ((rc = radix_pass(kA, sorted_ids, N, 8, 8, kB, vB, scratch, ST))) return rc;
-    if ((rc = radix_pass(kB, vB, N, 16, 8, kA, sorted_ids, scratch, ST))) return rc;
-    if ((rc = radix_pass(kA, sorted_ids, N, 24, 8, kB, vB, scratch, ST))) return rc;
+    if ((rc = radix_pass(dk, nullptr, N, 0, 11, kA, vB, scratch, ST))) return rc;
+    if ((rc = radix_pass(kA, vB, N, 11, 11, kB, sorted_ids, scratch, ST))) return rc;
+    if ((rc = radix_pass(kB, sorted_ids, N, 22, 10, nullptr, vB, scratch, ST))) return rc;
     GCB_CUDA(cudaMemcpyAsync(sorted_ids, vB, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToDevice, ST));
     gather_i32_kernel<<<gcb_cdiv(N, 256), 256, 0, ST>>>(num_tiles_hit, sorted_ids, nth_sorted, N);
     return scan_i32(nth_sorted, cum_sorted, N, 1, scratch, ST);
@@ -635,7 +745,7 @@ extern "C" size_t gcb_bin_tiles_workspace_bytes(int N, long long M, int tile_bx,
     (void)N;
     (void)tile_bx;
     (void)tile_by;
-    return ((size_t)3 * M + radix_ws_ints(M, 10) + 64) * sizeof(int);
+    return ((size_t)3 * M + radix_ws_ints(M, 11) + 64) * sizeof(int);
 }
 
 extern "C" int gcb_bin_tiles(const float* xys, const float* depths, const int32_t* radii, const int32_t* sorted_ids,
@@ -663,7 +773,7 @@ extern "C" int gcb_bin_tiles(const float* xys, const float* depths, const int32_
     while ((1 << bits_total) < ntiles) ++bits_total;
     int rc;
     const uint32_t* tile_sorted;
-    if (bits_total <= 10) {
+    if (bits_total <= 11) {
         if ((rc = radix_pass(tA, gA, M, 0, bits_total, tB, gaussian_ids, scratch, ST))) return rc;
         tile_sorted = tB;
     } else {

@@ -51,6 +51,17 @@ def render_gaussians(params: Dict[str, torch.Tensor], c2w: torch.Tensor, fx, fy,
     fovy = 2 * math.atan(H / (2 * fy))
     pm = projection_matrix(0.001, 1000, fovx, fovy)
     tile_bounds = ((W + 15) // 16, (H + 15) // 16, 1)
+    if (not training and not torch.is_grad_enabled() and sh_degree_active >= 0 and params["features_rest"].shape[1] == 15
+            and gsplat_ops.FUSED_EVAL):
+        # eval path (render_reverse, ns-gaussctrl-render): fused front end on the raw parameters
+        res = gsplat_ops.render_eval_fused(params, vm, pm @ vm, c2w.detach().to("cpu", torch.float32)[:3, 3].tolist(),
+                                           fx, fy, cx, cy, H, W, sh_degree_active, background)
+        if res is None:
+            return {"rgb": background.repeat(H, W, 1)}
+        rgb, depth, alpha, xys, radii = res
+        if state is not None:
+            state["xys"], state["radii"] = xys, radii
+        return {"rgb": rgb, "depth": depth, "accumulation": alpha}
     quats = params["quats"]
     colors = torch.cat((params["features_dc"][:, None, :], params["features_rest"]), dim=1)
     xys, depths, radii, conics, nth, _ = gsplat_ops.project_gaussians(

@@ -14,6 +14,8 @@ from . import ops
 from ._lib import check, lib
 
 BLOCK = 16
+LAST_M = [0]        # intersections of the most recent binning (bench.py reports it with the raster roofline)
+FUSED_EVAL = True  # GaussCtrlModel eval renders use the fused project+SH front end (gc_model.render_gaussians)
 _p = ops._p
 _stream = ops._stream
 
@@ -71,6 +73,7 @@ def bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds, want_keys: bool
     check(lib.gcb_depth_order(_p(depths), _p(num_tiles_hit), N, _p(sorted_ids), _p(cum), _p(ws), nb, _stream()))
     ops.LAUNCHES[0] += 16
     M = int(cum[-1].item())  # the one host sync gsplat's rasterize_gaussians also has
+    LAST_M[0] = M
     gids = torch.empty((max(M, 1),), dtype=torch.int32, device=dev)
     bins = torch.empty((tbx * tby, 2), dtype=torch.int32, device=dev)
     keys = torch.empty((max(M, 1),), dtype=torch.int64, device=dev) if want_keys else None
@@ -200,6 +203,43 @@ def rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, colors, opaci
     img, alpha = _RasterizeGaussians.apply(xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height,
                                            img_width, background)
     return (img, alpha) if return_alpha else img
+
+
+def render_eval_fused(params, viewmat, projmat, cam_origin, fx, fy, cx, cy, img_height, img_width, sh_degree,
+                      background):
+    """Eval-mode get_outputs in 3 stages on raw splatfacto parameters: fused project+SH+activations (one pass over the
+    236 B/Gaussian record), binning, fused rgb+depth composite + epilogue.
+    -> (rgb [H,W,3], depth [H,W,1], alpha [H,W,1], xys, radii) or None when nothing is visible."""
+    means = _f32(params["means"])
+    N, dev = means.shape[0], means.device
+    H, W = int(img_height), int(img_width)
+    tbx, tby = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
+    xys = torch.empty((N, 2), dtype=torch.float32, device=dev)
+    depths = torch.empty((N,), dtype=torch.float32, device=dev)
+    radii = torch.empty((N,), dtype=torch.int32, device=dev)
+    conics = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    nth = torch.empty((N,), dtype=torch.int32, device=dev)
+    rgbd = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    opac = torch.empty((N,), dtype=torch.float32, device=dev)
+    org = (ctypes.c_float * 3)(*[float(v) for v in cam_origin])
+    rest = params.get("features_rest")
+    check(lib.gcb_project_sh_fused_fwd(_p(means), _p(_f32(params["scales"])), _p(_f32(params["quats"])),
+                                       _p(_f32(params["features_dc"])), _p(None if rest is None else _f32(rest)),
+                                       _p(_f32(params["opacities"]).reshape(-1)), _host16(viewmat), _host16(projmat), org,
+                                       float(fx), float(fy), float(cx), float(cy), H, W, tbx, tby, int(sh_degree), N,
+                                       _p(xys), _p(depths), _p(radii), _p(conics), _p(nth), _p(rgbd), _p(opac), _stream()))
+    ops.LAUNCHES[0] += 1
+    gids, bins, _, M = bin_and_sort(xys, depths, radii, nth, (tbx, tby, 1))
+    if M < 1:
+        return None
+    bg4 = torch.cat([background.detach().to("cpu", torch.float32).reshape(3), torch.zeros(1)])
+    img4, fT, _ = rasterize_sorted(xys, conics, rgbd, opac, gids, bins, H, W, bg4)
+    rgb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((H, W, 1), dtype=torch.float32, device=dev)
+    alpha = torch.empty((H, W, 1), dtype=torch.float32, device=dev)
+    check(lib.gcb_raster_finalize(_p(img4), _p(fT), _p(rgb), _p(depth), _p(alpha), H * W, _stream()))
+    ops.LAUNCHES[0] += 1
+    return rgb, depth, alpha, xys, radii
 
 
 def rasterize_rgbd(xys, depths, radii, conics, num_tiles_hit, rgbs, opacity, img_height, img_width, background):

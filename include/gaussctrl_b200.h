@@ -154,6 +154,17 @@ int gcb_project_gaussians_fwd(const float* means3d, const float* scales, float g
 
 /* gsplat.spherical_harmonics forward: viewdirs [N,3] (unit), coeffs [N,K,3], colors [N,3]. */
 int gcb_sh_fwd(int degree, int K, const float* viewdirs, const float* coeffs, float* colors, int N, void* stream);
+/* Fused eval-path front end of GaussCtrlModel.get_outputs (gc_model.py:138-167): exp(scales), quats / |quats|,
+ * projection, view direction from h_cam_origin (host float[3]), SH colour (+0.5, clamp >= 0) and sigmoid(opacity) in
+ * ONE pass over the 236 B/Gaussian splatfacto parameter record.  Outputs as gcb_project_gaussians_fwd (no cov3d) plus
+ * rgbd [N,4] = (r, g, b, depth) - the 4-channel colour of the fused rgb+depth composite - and opac [N]. */
+int gcb_project_sh_fused_fwd(const float* means3d, const float* log_scales, const float* quats,
+                             const float* features_dc, const float* features_rest, const float* opacity_logits,
+                             const float* h_viewmat, const float* h_projmat, const float* h_cam_origin, float fx,
+                             float fy, float cx, float cy, int img_h, int img_w, int tile_bx, int tile_by,
+                             int sh_degree, int N, float* xys, float* depths, int32_t* radii, float* conics,
+                             int32_t* num_tiles_hit, float* rgbd, float* opac, void* stream);
+
 /* Inclusive prefix sum (torch.cumsum inside gsplat.rasterize_gaussians); workspace via gcb_scan_workspace_bytes. */
 size_t gcb_scan_workspace_bytes(int N);
 int gcb_cumsum_i32(const int32_t* in, int32_t* out, int N, void* workspace, size_t workspace_bytes, void* stream);

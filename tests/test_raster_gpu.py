@@ -142,6 +142,28 @@ def test_get_outputs_fused_rgbd():
     assert torch.equal(d_g[want["accumulation"] == 0], d_w[want["accumulation"] == 0])  # 1000 where nothing was hit
 
 
+def test_get_outputs_fused_front_end():
+    """Eval renders under no_grad go through the fused project+SH+activation kernel on the raw parameters: same image
+    as the gsplat-seam path and as the oracle."""
+    from oracle import gsplat_ref as gr
+    from gaussctrl_b200.gc_model import render_gaussians
+    N, H, W = 4000, 96, 80
+    P = _scene(N, seed=13)
+    c2w, fx, fy, cx, cy = _camera(H, W)
+    bg = torch.tensor([0.2, 0.4, 0.1])
+    want = gr.get_outputs(P, c2w, fx, fy, cx, cy, H, W, 3, bg)
+    Pc = {k: v.cuda() for k, v in P.items()}
+    seam = render_gaussians(Pc, c2w, fx, fy, cx, cy, H, W, 3, bg.cuda())
+    with torch.no_grad():
+        fused = render_gaussians(Pc, c2w, fx, fy, cx, cy, H, W, 3, bg.cuda())
+    torch.cuda.synchronize()
+    for k in ("rgb", "accumulation"):
+        assert (fused[k].cpu() - want[k]).abs().max().item() < 5e-5
+        assert (fused[k] - seam[k]).abs().max().item() < 5e-5
+    solid = want["accumulation"] > 1e-3
+    assert ((fused["depth"].cpu() - want["depth"]).abs() / want["depth"].abs().clamp(min=1e-3))[solid].max().item() < 1e-3
+
+
 def test_backward_matches_oracle_autograd():
     """Training-mode render + backward (the 3DGS fine-tune step) through the gsplat-seam autograd
     Functions vs autograd of the oracle restatement, for every Gaussian parameter group."""
