@@ -105,5 +105,6 @@ def test_render_reverse_and_edit_images_match_oracle():
             worst = max(worst, err.mean().item())
             assert err.mean().item() < 1e-2 and err.max().item() < 0.15, (j, err.mean().item(), err.max().item())
             outside = torch.from_numpy(~disc)
-            assert torch.equal(td[j]["image"][outside], rgb_un[j].float()[outside])  # mask composite keeps the original
+            # the mask composite keeps this run's own un-edited render bit for bit outside the mask (gc_pipeline.py:227-232)
+            assert torch.equal(td[j]["image"][outside], td[j]["unedited_image"].float()[outside])
     print("worst mean abs image error", worst)
