@@ -106,13 +106,13 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- reference arm (CPU)
-def reference_step_cpu(models, seed: int = 0):
-    """One DDIM step of one reference-schedule chunk (R=4 refs + c=3 views, CFG batch 14, literal 5-pass attention)
-    on the host cores.  Returns seconds."""
+def reference_step_cpu(models, seed: int = 0, chunk: int = CHUNK):
+    """One DDIM step of one reference-schedule chunk (R=4 refs + `chunk` views, CFG batch 2(R+chunk), literal 5-pass
+    attention) on the host cores.  Returns seconds."""
     from oracle import pipeline as opipe, sd15
     unet, cnet = models
     g = torch.Generator().manual_seed(seed)
-    F = REFS + CHUNK
+    F = REFS + chunk
     lat = torch.randn((F, 4, HW_LAT, HW_LAT), generator=g)
     disp = torch.rand((F, 1, HW_IMG, HW_IMG), generator=g).repeat(1, 3, 1, 1)
     pos, neg = torch.randn((1, 77, 768), generator=g), torch.randn((1, 77, 768), generator=g)
@@ -128,12 +128,15 @@ def run_reference(args):
     from oracle import sd15
     unet, cnet, _ = sd15.seeded_models(seed=0, with_vae=False)
     cores = torch.get_num_threads()
+    # bounded sample: the full chunk (c=3) when few steps are requested, a 1-view chunk otherwise, so that the whole
+    # --steps/--warmup run stays within a few minutes on the host cores (cost is proportional to the CFG batch)
+    c_s = CHUNK if args.steps + args.warmup <= 4 else 1
     for _ in range(args.warmup):
-        reference_step_cpu((unet, cnet))
-    times = [reference_step_cpu((unet, cnet)) for _ in range(args.steps)]
+        reference_step_cpu((unet, cnet), chunk=c_s)
+    times = [reference_step_cpu((unet, cnet), chunk=c_s) for _ in range(args.steps)]
     t = sum(times) / len(times)
-    vps = CHUNK / (t * S_STEPS)  # a chunk edits c views in S such steps (VAE decode and rasterisation not counted)
-    sample = (f"1 DDIM step of one reference-schedule chunk (R={REFS}+c={CHUNK} frames, CFG batch {2 * (REFS + CHUNK)}, "
+    vps = c_s / (t * S_STEPS)  # a chunk edits c views in S such steps (VAE decode and rasterisation not counted)
+    sample = (f"1 DDIM step of one reference-schedule chunk (R={REFS}+c={c_s} frames, CFG batch {2 * (REFS + c_s)}, "
               f"literal 5-pass attention, fp32) per step; views/s = c / (S x t_step), S={S_STEPS}")
     line = {"impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -323,10 +326,10 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import sd15
         un, cn, _ = sd15.seeded_models(seed=0, with_vae=False)
-        t = reference_step_cpu((un, cn))
-        cpu = {"value": CHUNK / (t * S_STEPS), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 DDIM step of one reference-schedule chunk (R={REFS}+c={CHUNK}, CFG batch 14, fp32 oracle): "
-                         f"{t:.1f} s; views/s = c / (S x t_step)"}
+        t = reference_step_cpu((un, cn), chunk=1)
+        cpu = {"value": 1 / (t * S_STEPS), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 DDIM step of one reference-schedule chunk (R={REFS} refs + c=1 view, CFG batch 10, literal "
+                         f"5-pass attention, fp32 oracle): {t:.1f} s; views/s = c / (S x t_step), S={S_STEPS}"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
