@@ -9,7 +9,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgaussctrl_b200.so")
+LIB_PATH = os.environ.get("GCB_LIB_PATH") or os.path.join(HERE, "libgaussctrl_b200.so")  # override: A/B builds
 
 GCB_ACT_NONE, GCB_ACT_SILU, GCB_ACT_GEGLU = 0, 1, 2
 GCB_GEMM_TCGEN05, GCB_GEMM_MMA_SYNC = 0, 1

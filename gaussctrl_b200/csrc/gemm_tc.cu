@@ -290,8 +290,14 @@ int choose_bn(int M, int N, int act) {
     const int cands[4] = {256, 160, 128, 64};
     int best = 64;
     long long best_pad = -1;
+    static int max_bn = -1;
+    if (max_bn < 0) {
+        const char* e = getenv("GCB_GEMM_MAX_BN");
+        max_bn = e ? atoi(e) : 256;
+    }
     for (int i = 0; i < 4; ++i) {
         const int bn = cands[i];
+        if (bn > max_bn) continue;
         const long long pad = (long long)gcb_cdiv(N, bn) * bn;
         if (best_pad < 0 || pad < best_pad) {
             best_pad = pad;
