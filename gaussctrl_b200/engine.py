@@ -215,7 +215,10 @@ class EditEngine:
         need = sorted(set(non_ref) | set(ref_indices))
         cond_map = {v: c for v, c in zip(need, self._cond_emb(disparity[need]))}
         # (1) reference pass
-        bsz = min(view_batch, max(1, len(non_ref)))
+        # balanced batches: the fewest batches of at most `view_batch` views, all of (almost) the same size, so the
+        # padding of the last batch is at most nb-1 views (39 views, view_batch 12 -> 4 batches of 10, not 12+12+12+3)
+        n_batches = max(1, -(-len(non_ref) // max(1, view_batch)))
+        bsz = max(1, -(-len(non_ref) // n_batches))
         world = dist_ctx["world"] if dist_ctx else 1
         key = ("refs_once", R, bsz, hw, float(guidance), tuple(ref_frames), world)
         if key not in self._steps:
@@ -232,7 +235,7 @@ class EditEngine:
         ref_step.x.copy_(x_all[list(ref_indices)])
         ref_step.set_cond(torch.stack([cond_map[v] for v in ref_indices]))
         # (2) view batches (the last one is padded by repeating its final view so one graph serves all)
-        batches: List[List[int]] = [non_ref[i:i + view_batch] for i in range(0, len(non_ref), view_batch)]
+        batches: List[List[int]] = [non_ref[i:i + bsz] for i in range(0, len(non_ref), bsz)]
         x_views: List[torch.Tensor] = []
         conds: List[torch.Tensor] = []
         for b in batches:
