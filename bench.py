@@ -316,8 +316,16 @@ def main():
         t_k = e0.elapsed_time(e1) / reps / 1e3
         flops = Bq * 5 * 4.0 * ATTN_N * ATTN_N * C
         ach = flops / t_k / 1e12
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of the same shape
+            tj = json.load(open(os.path.join(REPO, "profiles", "attn_ncu_traffic.json")))
+            if vb == 12:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "multi-source cross-view attention N=4096 d=40 (5 K/V sources)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes": float(Bq * ATTN_N * C * 2 * 4 + 2 * REFS * ATTN_N * 2 * C * 2),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                 "how": f"CUDA events around {reps} back-to-back launches at the workload's shape (B={Bq} rows)"}
 
