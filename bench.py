@@ -285,6 +285,17 @@ def main():
         e2e = {"value": V / (ms_e / args.steps / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes)}
 
+    # ---- stage A through the public API (extra, measured once): render_reverse() = rasterise + VAE encode + DDIM
+    #      inversion of every view, results written to host train_data (gc_pipeline.py:122-157)
+    stage_a_ms = None
+    if not args.no_e2e and world == 1:
+        pipe.render_reverse()  # warm-up: captures the inversion graphs
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pipe.render_reverse()
+        torch.cuda.synchronize()
+        stage_a_ms = (time.perf_counter() - t0) * 1e3
+
     # ---- dominant kernel: cross-view attention at (N=4096, d=40), 5 sources (self + 4 cached refs)
     roof = None
     if rank == 0:
@@ -352,6 +363,8 @@ def main():
                                              "the binning included); roofline bound = HBM"},
                           "schedule": "refs_once (reference views denoised once per DDIM step, K/V recorded)",
                           "view_batch": args.view_batch, "breakdown": breakdown,
+                          "render_reverse_ms": stage_a_ms,
+                          "views_per_s_stage_a_plus_b": (V / ((stage_a_ms + ms_per_step) / 1e3)) if stage_a_ms else None,
                           "views_total": V,
                           "multi_gpu": None if world == 1 else "views sharded round-robin; reference pass sharded over "
                                        "its 2R CFG rows with a per-layer NCCL all-gather of q|k|v"}}
