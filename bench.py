@@ -296,6 +296,36 @@ def main():
         torch.cuda.synchronize()
         stage_a_ms = (time.perf_counter() - t0) * 1e3
 
+    # ---- the step after the path (extra): 3DGS fine-tune iterations on the edited images
+    #      (gc_trainer.py:257-301: training render -> L1+SSIM -> backward -> Adam over 59 floats/Gaussian)
+    finetune = None
+    if not args.no_e2e and world == 1:
+        try:
+            import random as _random
+            from gaussctrl_b200.finetune import FineTuner
+            dm.device = dev
+            _random.seed(0)
+            tuner = FineTuner(model, dm)
+            for it in range(3):
+                tuner.train_iteration(30000 + it)
+            n_it = 20
+            e0, e1 = ev(), ev()
+            torch.cuda.synchronize()
+            l0 = ops.LAUNCHES[0]
+            e0.record()
+            for it in range(n_it):
+                tuner.train_iteration(30003 + it)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_it = e0.elapsed_time(e1) / n_it
+            finetune = {"iterations_per_s": 1e3 / ms_it, "ms_per_iteration": ms_it, "iterations": n_it,
+                        "launches_per_iteration": (ops.LAUNCHES[0] - l0) / n_it,
+                        "adam_algorithmic_bytes": 28.0 * 59 * args.gaussians,
+                        "note": "GaussCtrlModel.get_outputs (training) + get_loss_dict (fused L1+SSIM fwd/bwd) + "
+                                "backward + FusedAdam, one random view per iteration, reference lrs"}
+        except Exception as exc:  # an extra must never take the headline down
+            finetune = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     # ---- dominant kernel: cross-view attention at (N=4096, d=40), 5 sources (self + 4 cached refs)
     roof = None
     if rank == 0:
@@ -363,7 +393,7 @@ def main():
                                              "the binning included); roofline bound = HBM"},
                           "schedule": "refs_once (reference views denoised once per DDIM step, K/V recorded)",
                           "view_batch": args.view_batch, "breakdown": breakdown,
-                          "render_reverse_ms": stage_a_ms,
+                          "render_reverse_ms": stage_a_ms, "finetune": finetune,
                           "views_per_s_stage_a_plus_b": (V / ((stage_a_ms + ms_per_step) / 1e3)) if stage_a_ms else None,
                           "views_total": V,
                           "multi_gpu": None if world == 1 else "views sharded round-robin; reference pass sharded over "

@@ -56,6 +56,7 @@ except Exception:  # ModuleNotFoundError here
         sh_degree: int = 3
         sh_degree_interval: int = 1000
         background_color: str = "random"
+        ssim_lambda: float = 0.2
 
     class SplatfactoModel(torch.nn.Module):
         """Owns the Gaussian parameters under the nerfstudio names (gc_model.py:124-136 reads them)."""
@@ -87,6 +88,18 @@ except Exception:  # ModuleNotFoundError here
 
         def set_crop(self, box):
             self.crop_box = box
+
+        def forward(self, camera):
+            return self.get_outputs(camera)
+
+        def get_gt_img(self, image: torch.Tensor) -> torch.Tensor:
+            return image.to(self.device)  # downscale factor 1 after step 30000 (resolution schedule finished)
+
+        @torch.no_grad()
+        def get_metrics_dict(self, outputs, batch):
+            gt = self.get_gt_img(batch["image"])
+            mse = torch.mean((outputs["rgb"].detach() - gt) ** 2)
+            return {"psnr": 10.0 * torch.log10(1.0 / mse), "gaussian_count": self.means.shape[0]}
 
     @dataclass
     class VanillaPipelineConfig:

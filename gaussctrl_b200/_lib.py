@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCB_LIB_PATH") or os.path.join(HERE, "libgaussctrl_b200.so")  # override: A/B builds
@@ -64,6 +64,10 @@ SIGNATURES = {
                                           _P, _P, _P, _P, c_int, _P, _P, _P, _P]),
     "gcb_sh_bwd": (c_int, [c_int, c_int, _P, _P, _P, c_int, _P]),
     "gcb_raster_finalize": (c_int, [_P, _P, _P, _P, _P, c_int, _P]),
+    "gcb_l1_ssim_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gcb_l1_ssim_loss_fwd_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
+    "gcb_adam_step": (c_int, [c_int, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_longlong),
+                              POINTER(c_double), c_double, c_double, c_double, c_int, _P]),
 }
 
 

@@ -132,6 +132,17 @@ class GaussCtrlModel(SplatfactoModel):
         self.xys, self.radii = state.get("xys"), state.get("radii")
         return out
 
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
+        """nerfstudio 1.0.0 SplatfactoModel.get_loss_dict (what gc_pipeline.py:283-285 calls; the reference's
+        GaussCtrlModel inherits it): main_loss = (1-l)*L1 + l*(1-SSIM) with the loss AND its gradient w.r.t. the
+        render from one fused C-ABI call (finetune.l1_ssim_loss).  Scale regularisation is off in the reference's
+        config (use_scale_regularization default False) -> 0."""
+        from .finetune import l1_ssim_loss
+        gt = self.get_gt_img(batch["image"]) if hasattr(self, "get_gt_img") else batch["image"].to(self.device)
+        main_loss, parts = l1_ssim_loss(outputs["rgb"], gt, float(getattr(self.config, "ssim_lambda", 0.2)))
+        self.last_loss_parts = parts  # device float[3]: (main_loss, L1, ssim) - no host sync here
+        return {"main_loss": main_loss, "scale_reg": torch.zeros((), device=main_loss.device)}
+
     @torch.no_grad()
     def get_outputs_for_camera(self, camera: Cameras, obb_box=None) -> Dict[str, torch.Tensor]:
         assert camera is not None, "must provide camera to gaussian model"

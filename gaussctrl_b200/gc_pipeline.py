@@ -245,3 +245,13 @@ class SimpleDataManager:
         self.cameras = cameras
         n = len(cameras)
         self.train_data = train_data if train_data is not None else [{"image_idx": i} for i in range(n)]
+        self.train_unseen_cameras = list(range(n))
+        self.device = "cuda"
+
+    def next_train(self, step: int):
+        """gc_datamanager.py:213-235: a random not-yet-seen view and a copy of its train_data entry."""
+        from .finetune import next_train_view
+        idx = next_train_view(self.train_unseen_cameras, len(self.train_data))
+        data = dict(self.train_data[idx])
+        data["image"] = torch.as_tensor(data["image"]).to(self.device)
+        return self.cameras[idx:idx + 1].to(self.device), data

@@ -221,6 +221,30 @@ int gcb_sh_bwd(int degree, int K, const float* viewdirs, const float* v_colors, 
 int gcb_raster_finalize(const float* img4, const float* final_T, float* rgb, float* depth, float* alpha, int HW,
                         void* stream);
 
+/* ======================================================================================================
+ * C. 3DGS fine-tune step that follows the edit – replaces the eager torch ops behind
+ *    `loss_dict = model.get_loss_dict(...)`, `loss.backward()` and `optimizers.optimizer_scaler_step_some(...)`
+ *    in GaussCtrlTrainer.train_iteration (gaussctrl/gc_trainer.py:257-301; get_train_loss_dict
+ *    gaussctrl/gc_pipeline.py:276-287; Adam groups gaussctrl/gc_config.py:57-89).
+ * ====================================================================================================== */
+
+/* nerfstudio SplatfactoModel.get_loss_dict main_loss and its gradient in one call:
+ *     main_loss = (1-ssim_lambda) * mean|gt-pred| + ssim_lambda * (1 - SSIM(gt, pred))
+ * SSIM as pytorch_msssim (11-tap Gaussian sigma 1.5, valid blur, K=(0.01,0.03), data_range 1, mean over map).
+ * pred, gt [H,W,C] fp32 channels-last (H, W >= 11).  loss_out: DEVICE float[3] = (main_loss, L1, ssim);
+ * v_pred [H,W,C] = d main_loss / d pred.  Deterministic (no atomics).  No host sync. */
+size_t gcb_l1_ssim_workspace_bytes(int H, int W, int C);
+int gcb_l1_ssim_loss_fwd_bwd(const float* pred, const float* gt, int H, int W, int C, float ssim_lambda,
+                             float* loss_out, float* v_pred, void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.optim.Adam step (no weight decay, no amsgrad) over n_tensors fp32 tensors in one launch per 8 tensors.
+ * h_* are HOST arrays of n_tensors entries: device pointers of param / grad / exp_avg / exp_avg_sq (16-byte
+ * aligned), element counts, and the learning rate of each tensor (one nerfstudio optimizer group per tensor).
+ * step counts from 1 (bias corrections 1-beta^step are computed on the host in double, as torch does). */
+int gcb_adam_step(int n_tensors, void* const* h_params, const void* const* h_grads, void* const* h_exp_avg,
+                  void* const* h_exp_avg_sq, const long long* h_numel, const double* h_lr, double beta1, double beta2,
+                  double eps, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
