@@ -109,9 +109,11 @@ class GaussCtrlPipeline(VanillaPipeline):
 
     @staticmethod
     def _load_weights(ckpt: str, seed: int):
+        """A local diffusers-layout folder is loaded (checkpoint.py); a hub name such as the default
+        "CompVis/stable-diffusion-v1-4" cannot be resolved without network: seeded synthetic weights stand in."""
         if os.path.isdir(ckpt):
-            raise NotImplementedError("loading safetensors checkpoints: key names already match sd15_spec; wire "
-                                      "safetensors.torch.load_file here when a checkpoint is on disk")
+            from .checkpoint import load_diffusers_checkpoint
+            return load_diffusers_checkpoint(ckpt)
         return synthetic_weights(seed)
 
     # ------------------------------------------------------------------------------------------ stage A
@@ -224,6 +226,19 @@ class GaussCtrlPipeline(VanillaPipeline):
         td["z_0_image"] = latent.cpu().to(torch.float32).numpy()
         if mask is not None:
             td["mask_image"] = mask
+
+    # ---- B200 extension: stage-A products on disk in the reference's folder layout (store.py)
+    def save_stage_a(self, root: str) -> None:
+        from . import store
+        store.save_train_data(root, self.datamanager.train_data)
+
+    def load_stage_a(self, root: str) -> bool:
+        """Fill train_data from `root` (depth_npy/, z_0/, mask_npy/, unedited/); True when edit_images can run without
+        render_reverse."""
+        from . import store
+        store.load_train_data(root, len(self.datamanager.train_data), self.datamanager.train_data,
+                              load_mask=self.config.langsam_obj != "")
+        return store.has_stage_a(root)
 
     def get_train_loss_dict(self, step: int):
         ray_bundle, batch = self.datamanager.next_train(step)
