@@ -66,6 +66,9 @@ SIGNATURES = {
     "gcb_raster_finalize": (c_int, [_P, _P, _P, _P, _P, c_int, _P]),
     "gcb_l1_ssim_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gcb_l1_ssim_loss_fwd_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
+    "gcb_embed_tokens_f16": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "gcb_quick_gelu_fwd": (c_int, [_P, _P, c_longlong, _P]),
+    "gcb_attn_causal_fwd": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P]),
     "gcb_adam_step": (c_int, [c_int, POINTER(_P), POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_longlong),
                               POINTER(c_double), c_double, c_double, c_double, c_int, _P]),
 }

@@ -94,6 +94,9 @@ class GaussCtrlPipeline(VanillaPipeline):
         self.vae = VaeB200(vae_sd, self.device_) if vae_sd is not None else None
         self.tables = DDIMTables()
         self.engine = EditEngine(self.denoiser, self.tables)
+        if prompt_encoder is None and os.path.isdir(config.diffusion_ckpt):
+            from .clip_text import make_prompt_encoder   # real tokenizer + CLIP text encoder on the B200 kernels
+            prompt_encoder = make_prompt_encoder(config.diffusion_ckpt, self.device_)
         self.prompt_encoder = prompt_encoder or synthetic_prompt_embeds
         self.positive_prompt = self.edit_prompt + ", " + ADDED_PROMPT
         self.positive_reverse_prompt = self.reverse_prompt + ", " + ADDED_PROMPT

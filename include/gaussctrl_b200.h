@@ -245,6 +245,25 @@ int gcb_adam_step(int n_tensors, void* const* h_params, const void* const* h_gra
                   void* const* h_exp_avg_sq, const long long* h_numel, const double* h_lr, double beta1, double beta2,
                   double eps, int step, void* stream);
 
+/* ======================================================================================================
+ * D. Prompt side – the CLIP text encoder diffusers runs inside `self.pipe(prompt=...,
+ *    negative_prompt=...)` (gaussctrl/gc_pipeline.py:142-145, :209-219 -> encode_prompt -> CLIPTextModel).
+ *    Projections / LayerNorm reuse gcb_conv2d_nhwc_fwd / gcb_layernorm_fwd; these are the remaining pieces.
+ * ====================================================================================================== */
+
+/* out[b,t,:] = tok_emb[ids[b,t],:] + pos_emb[t,:]   (fp16 tables [vocab,C] / [T,C]; ids DEVICE int32 [B,T],
+ * clamped to the table). */
+int gcb_embed_tokens_f16(const int32_t* ids, const void* tok_emb, const void* pos_emb, void* out, int B, int T, int C,
+                         int vocab, void* stream);
+
+/* y = x * sigmoid(1.702 x) (CLIP "quick_gelu"), fp16, n a multiple of 8. */
+int gcb_quick_gelu_fwd(const void* x, void* y, long long n, void* stream);
+
+/* Causal (lower-triangular) self-attention for short sequences: q,k,v [B,T,heads*d] slices with row stride ld_qkv
+ * (a fused q|k|v projection), out [B,T,heads*d] with row stride ld_out; T <= 128, d = 64; fp32 softmax. */
+int gcb_attn_causal_fwd(const void* q, const void* k, const void* v, int ld_qkv, void* out, int ld_out, int B, int T,
+                        int heads, int d, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,69 @@
+"""GPU parity of the CLIP text encoder on the sm_100a kernels (gaussctrl_b200/clip_text.py, csrc/clip.cu) against
+oracle/clip_text.py, which tests/test_clip_cpu.py pins to the real transformers.CLIPTextModel."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float().cpu() - b.float()).norm() / b.float().norm()).item()
+
+
+def test_embed_tokens_and_quick_gelu():
+    from gaussctrl_b200 import ops
+    from gaussctrl_b200._lib import check, lib
+    g = torch.Generator().manual_seed(0)
+    tok, pos = torch.randn((1000, 768), generator=g).half(), torch.randn((77, 768), generator=g).half()
+    ids = torch.randint(0, 1000, (3, 77), generator=g, dtype=torch.int32)
+    out = torch.empty((3, 77, 768), dtype=torch.float16, device="cuda")
+    check(lib.gcb_embed_tokens_f16(ops._p(ids.cuda()), ops._p(tok.cuda()), ops._p(pos.cuda()), ops._p(out), 3, 77, 768, 1000,
+                                   ops._stream()))
+    want = (tok[ids.long()].float() + pos.float()).half()
+    assert torch.equal(out.cpu(), want)
+    x = (torch.randn((5, 77, 3072), generator=g) * 3).half()
+    y = torch.empty_like(x, device="cuda")
+    check(lib.gcb_quick_gelu_fwd(ops._p(x.cuda()), ops._p(y), x.numel(), ops._stream()))
+    wantg = x.float() * torch.sigmoid(1.702 * x.float())
+    assert (y.cpu().float() - wantg).abs().max().item() < 4e-3 and _rel(y, wantg) < 1e-3
+
+
+@pytest.mark.parametrize("B,T", [(2, 77), (1, 128), (3, 1), (2, 33)])
+def test_causal_attention(B, T):
+    from gaussctrl_b200 import ops
+    from gaussctrl_b200._lib import check, lib
+    heads, d = 12, 64
+    C = heads * d
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn((B, T, 3 * C), generator=g).half()
+    out = torch.empty((B, T, C), dtype=torch.float16, device="cuda")
+    dq = qkv.cuda()
+    check(lib.gcb_attn_causal_fwd(ops._p(dq), ops._p(dq, C), ops._p(dq, 2 * C), 3 * C, ops._p(out), C, B, T, heads, d,
+                                  d ** -0.5, ops._stream()))
+    q, k, v = (qkv[..., i * C:(i + 1) * C].float().reshape(B, T, heads, d).transpose(1, 2) for i in range(3))
+    want = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, T, C)
+    assert _rel(out, want) < 1e-3
+    # row 0 attends to itself only: out[:, 0] == v[:, 0] exactly (p = 1, l = 1)
+    assert torch.equal(out[:, 0].cpu(), qkv[:, 0, 2 * C:])
+
+
+@pytest.mark.parametrize("layers", [2, 12])
+def test_clip_text_encoder_matches_oracle(layers):
+    from oracle import clip_text as oc
+    from gaussctrl_b200.clip_text import ClipTextB200
+    sd = {k: v.half().float() for k, v in oc.seeded_state_dict(seed=7, layers=layers).items()}
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, oc.VOCAB, (2, 77), generator=g)
+    ids[:, 0] = 49406
+    ids[1, 12:] = 49407
+    want = oc.clip_text_forward(sd, ids, layers=layers)
+    enc = ClipTextB200(sd, "cuda", layers=layers)
+    got = enc.encode(ids)
+    assert got.shape == (2, 77, 768) and got.dtype == torch.float16
+    rel = _rel(got, want)
+    assert rel < 1e-2, rel   # fp16 residual stream through `layers` blocks vs fp32
+    # batch invariance / causality through the whole stack: later tokens do not change earlier embeddings
+    ids2 = ids.clone()
+    ids2[:, 50:] = 777
+    got2 = enc.encode(ids2)
+    assert torch.equal(got2[:, :50], got[:, :50])
