@@ -17,13 +17,15 @@ def test_embed_tokens_and_quick_gelu():
     tok, pos = torch.randn((1000, 768), generator=g).half(), torch.randn((77, 768), generator=g).half()
     ids = torch.randint(0, 1000, (3, 77), generator=g, dtype=torch.int32)
     out = torch.empty((3, 77, 768), dtype=torch.float16, device="cuda")
-    check(lib.gcb_embed_tokens_f16(ops._p(ids.cuda()), ops._p(tok.cuda()), ops._p(pos.cuda()), ops._p(out), 3, 77, 768, 1000,
+    d_ids, d_tok, d_pos = ids.cuda(), tok.cuda(), pos.cuda()   # keep the device buffers alive across the launch
+    check(lib.gcb_embed_tokens_f16(ops._p(d_ids), ops._p(d_tok), ops._p(d_pos), ops._p(out), 3, 77, 768, 1000,
                                    ops._stream()))
     want = (tok[ids.long()].float() + pos.float()).half()
     assert torch.equal(out.cpu(), want)
     x = (torch.randn((5, 77, 3072), generator=g) * 3).half()
-    y = torch.empty_like(x, device="cuda")
-    check(lib.gcb_quick_gelu_fwd(ops._p(x.cuda()), ops._p(y), x.numel(), ops._stream()))
+    d_x = x.cuda()
+    y = torch.empty_like(d_x)
+    check(lib.gcb_quick_gelu_fwd(ops._p(d_x), ops._p(y), x.numel(), ops._stream()))
     wantg = x.float() * torch.sigmoid(1.702 * x.float())
     assert (y.cpu().float() - wantg).abs().max().item() < 4e-3 and _rel(y, wantg) < 1e-3
 

@@ -76,11 +76,13 @@ def test_fused_adam_matches_torch_adam():
         opt_ref.step()
         opt.step()
     for i, (p, q) in enumerate(zip(ref, mine)):
-        assert torch.allclose(q.detach().cpu(), p.detach(), rtol=2e-6, atol=2e-6 * lrs[i] * 6), i
+        # fp32 round-off only: a few ulps of the largest value of each tensor
+        assert (q.detach().cpu() - p.detach()).abs().max().item() <= 2e-6 * max(1.0, p.detach().abs().max().item()), i
         st_r, st = opt_ref.state[p], opt.state[q]
-        assert int(st["step"]) == int(st_r["step"])
-        assert torch.allclose(st["exp_avg"].cpu(), st_r["exp_avg"], rtol=1e-5, atol=1e-12)
-        assert torch.allclose(st["exp_avg_sq"].cpu(), st_r["exp_avg_sq"], rtol=1e-5, atol=1e-20)
+        assert int(st["step"]) == int(st_r["step"]) == (5 if i == 3 else 6)
+        for key in ("exp_avg", "exp_avg_sq"):
+            err = (st[key].cpu() - st_r[key]).abs().max().item()
+            assert err <= 1e-5 * st_r[key].abs().max().item(), (i, key, err)
     # state_dict round trip with torch.optim.Adam's key names
     sd = opt.state_dict()
     assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
