@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GCB_LIB_PATH") or os.path.join(HERE, "libgaussctrl_b200.so")  # override: A/B builds
 
 GCB_ACT_NONE, GCB_ACT_SILU, GCB_ACT_GEGLU = 0, 1, 2
-GCB_GEMM_TCGEN05, GCB_GEMM_MMA_SYNC = 0, 1
+GCB_GEMM_TCGEN05, GCB_GEMM_MMA_SYNC, GCB_GEMM_TCGEN05_DIRECT = 0, 1, 2
 GCB_ATTN_AUTO, GCB_ATTN_TCGEN05, GCB_ATTN_MMA_SYNC = 0, 1, 2
 
 _P = c_void_p

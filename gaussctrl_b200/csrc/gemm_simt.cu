@@ -9,7 +9,7 @@
 int gcb_gemm_tc_supported(int B, int H, int W, int Cin, int Cout, int ksize, int act);
 int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
                        const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
-                       cudaStream_t stream);
+                       int direct_epilogue, cudaStream_t stream);
 
 namespace {
 
@@ -232,13 +232,14 @@ extern "C" int gcb_conv2d_nhwc_fwd(const void* x, const void* w, const void* bia
     GCB_CHECK_ARG((long long)B * H * W < (1ll << 31), "M too large");
     cudaStream_t st = (cudaStream_t)stream;
     if (const char* e = getenv("GCB_FORCE_GEMM_IMPL")) impl = atoi(e);
-    if (impl == GCB_GEMM_TCGEN05) {
+    if (impl == GCB_GEMM_TCGEN05 || impl == GCB_GEMM_TCGEN05_DIRECT) {
         if (!gcb_gemm_tc_supported(B, H, W, Cin, Cout, ksize, act)) {
             gcb_set_error("tcgen05 path does not support B=%d H=%d W=%d Cin=%d Cout=%d k=%d act=%d", B, H, W, Cin, Cout,
                           ksize, act);
             return GCB_ERR_UNSUPPORTED;
         }
-        return gcb_gemm_tc_launch(x, w, bias, rowvec, rowvec_ld, residual, y, B, H, W, Cin, Cout, ksize, act, st);
+        return gcb_gemm_tc_launch(x, w, bias, rowvec, rowvec_ld, residual, y, B, H, W, Cin, Cout, ksize, act,
+                                  impl == GCB_GEMM_TCGEN05_DIRECT, st);
     }
     GCB_CHECK_ARG(impl == GCB_GEMM_MMA_SYNC, "unknown impl %d", impl);
     GCB_CHECK_ARG(act != GCB_ACT_GEGLU, "GEGLU epilogue exists only on the tcgen05 path");

@@ -36,12 +36,29 @@ struct GemmTcParams {
     __half* y;
     int ldy;
     int act;
+    int epi;           // 0 = each thread stores its own row (64 B pieces); 1 = 32x64 tiles staged in smem + TMA store
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == GCB_ACT_SILU ? silu_f(v) : v; }
 
+// Epilogue staging (p.epi = 1): once tmem_full_bar has fired every MMA has consumed its operands, so the TMA ring is
+// free: epilogue warp q owns two 4 KB buffers at ring offset q * 8 KB.  A buffer is one 32-row x 64-column fp16 tile in
+// the 128B-swizzled layout of the output tensor map: row r at r * 128 B, 16-byte piece j at (j ^ (r & 7)) * 16 -
+// conflict-free for "one row per thread" writes - and leaves through ONE cp.async.bulk.tensor store of full 128 B
+// lines instead of 32 lanes x 4 scattered 16 B stores (32 L1 wavefronts per instruction).
+__device__ __forceinline__ void stage_row_half(uint32_t buf, int lane, int half, const float (&v)[32]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int j = half * 4 + g;
+        st_shared_v4(buf + (uint32_t)(lane * 128) + (uint32_t)((j ^ (lane & 7)) << 4), pack_half2(v[g * 8 + 0], v[g * 8 + 1]),
+                     pack_half2(v[g * 8 + 2], v[g * 8 + 3]), pack_half2(v[g * 8 + 4], v[g * 8 + 5]),
+                     pack_half2(v[g * 8 + 6], v[g * 8 + 7]));
+    }
+}
+
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      const __grid_constant__ CUtensorMap tmY, const GemmTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -145,6 +162,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool row_ok = m < p.M;
         const int img = (p.rowvec != nullptr && row_ok) ? (int)(m / p.HW) : 0;
+        const bool issuer = elect_one_sync() != 0;            // the one lane that issues / waits on this warp's TMA stores
+        const uint32_t stage_buf = smem_base + (uint32_t)q * 8192u;
+        const int y_row0 = m_tile * BM + q * 32;
+        int n_pairs = 0;                                        // staged 64-column groups so far (buffer = n_pairs & 1)
         if (p.act != GCB_ACT_GEGLU) {
             const int nchunks = p.BN / 32;
             const int ncol0 = n_tile * p.BN;
@@ -163,8 +184,17 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             load_res(0, res_cur);
             mbar_wait(smem_u32(&tmem_full_bar), 0);
             tc_fence_after();
+            if (p.epi) fence_proxy_async_smem();  // generic writes below follow the TMA (async proxy) fills of the ring
+            bool pair_staged = false;
             for (int c = 0; c < nchunks; ++c) {
                 const int n0 = ncol0 + c * 32;
+                if ((c & 1) == 0) {
+                    pair_staged = p.epi && c + 1 < nchunks && n0 + 64 <= p.N;
+                    if (pair_staged && n_pairs >= 2) {  // the store that last used this buffer must have read it
+                        if (issuer) tma_store_wait_read<1>();
+                        __syncwarp();
+                    }
+                }
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
                 if (c + 1 < nchunks) load_res(c + 1, res_nxt);
@@ -183,7 +213,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                     }
                 }
                 tc_wait_ld();
-                if (row_ok && n0 < p.N) {
+                if ((row_ok || pair_staged) && n0 < p.N) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -210,19 +240,23 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
                         }
-                        if (res_row) {
+                        if (res_row && row_ok) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) add8(res_cur[g], g);
                         }
-                        uint4* op = reinterpret_cast<uint4*>(yp);
+                        if (pair_staged) {
+                            stage_row_half(stage_buf + (uint32_t)((n_pairs & 1) * 4096), lane, c & 1, v);
+                        } else {
+                            uint4* op = reinterpret_cast<uint4*>(yp);
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 o;
-                            o.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]);
-                            o.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
-                            o.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]);
-                            o.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
-                            op[g] = o;
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 o;
+                                o.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]);
+                                o.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
+                                o.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]);
+                                o.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
+                                op[g] = o;
+                            }
                         }
                     } else {
                         const int nvalid = p.N - n0;
@@ -239,6 +273,15 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                         }
                     }
                 }
+                if (pair_staged && (c & 1)) {  // both halves of the 32 x 64 tile are in smem: one bulk store
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (issuer) {
+                        tma_store_2d(&tmY, stage_buf + (uint32_t)((n_pairs & 1) * 4096), n0 - 32, y_row0);
+                        tma_store_commit();
+                    }
+                    ++n_pairs;
+                }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) res_cur[g] = res_nxt[g];
             }
@@ -248,14 +291,19 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             tc_fence_after();
             const int half_bn = p.BN / 2;
             const int n_out = p.N / 2;
+            if (p.epi) fence_proxy_async_smem();
             for (int c = 0; c < half_bn / 32; ++c) {
+                if (p.epi && (c & 1) == 0 && n_pairs >= 2) {
+                    if (issuer) tma_store_wait_read<1>();
+                    __syncwarp();
+                }
                 uint32_t rv[32], rg[32];
                 tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), rv);
                 tmem_ld_32x32b_x32(taddr + (uint32_t)(half_bn + c * 32), rg);
                 tc_wait_ld();
                 const int t0 = n_tile * p.BN;                 // packed-row offset of this tile
                 const int o0 = n_tile * half_bn + c * 32;     // output column
-                if (!row_ok || o0 >= n_out) continue;
+                if ((!row_ok && !p.epi) || o0 >= n_out) continue;
                 float o[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -266,6 +314,19 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                         gate += __half2float(p.bias[t0 + half_bn + c * 32 + j]);
                     }
                     o[j] = val * gelu_erf_f(gate);
+                }
+                if (p.epi) {  // half_bn / 32 is even and n_out % 64 == 0: every pair is a full 32 x 64 tile
+                    stage_row_half(stage_buf + (uint32_t)((n_pairs & 1) * 4096), lane, c & 1, o);
+                    if (c & 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (issuer) {
+                            tma_store_2d(&tmY, stage_buf + (uint32_t)((n_pairs & 1) * 4096), o0 - 32, y_row0);
+                            tma_store_commit();
+                        }
+                        ++n_pairs;
+                    }
+                    continue;
                 }
                 uint4* op = reinterpret_cast<uint4*>(p.y + m * p.ldy + o0);
 #pragma unroll
@@ -279,6 +340,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 }
             }
         }
+        if (p.epi && issuer) tma_store_wait_read<0>();  // smem must outlive the bulk stores that read it
     }
     tc_fence_before();
     __syncthreads();
@@ -344,7 +406,7 @@ int gcb_gemm_tc_supported(int B, int H, int W, int Cin, int Cout, int ksize, int
 
 int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
                        const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
-                       cudaStream_t stream) {
+                       int direct_epilogue, cudaStream_t stream) {
     GemmTcParams p;
     memset(&p, 0, sizeof(p));
     const long long M = (long long)B * H * W;
@@ -375,8 +437,11 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
     p.y = (__half*)y;
     p.ldy = (act == GCB_ACT_GEGLU) ? Cout / 2 : Cout;
     p.act = act;
+    // default: 32x64 output tiles staged in shared memory + TMA store; GCB_GEMM_TCGEN05_DIRECT keeps the round-1
+    // per-thread row stores for A/B measurements
+    p.epi = (!direct_epilogue && p.ldy >= 64) ? 1 : 0;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmY;
     int rc;
     if (p.mode == 0) {
         const uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)M};
@@ -400,6 +465,17 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
         rc = gcb_encode_tma(&tmB, w, 2, dims, strides, box, 1);
         if (rc != GCB_OK) return rc;
     }
+    {   // output: [M, ldy] fp16, 32-row x 64-column boxes, 128B swizzle; the box is clipped at M and ldy by the hardware
+        const uint64_t dims[2] = {(uint64_t)p.ldy, (uint64_t)M};
+        const uint64_t strides[1] = {(uint64_t)p.ldy * 2};
+        const uint32_t box[2] = {64, 32};
+        if (p.epi) {
+            rc = gcb_encode_tma(&tmY, y, 2, dims, strides, box, 1);
+            if (rc != GCB_OK) return rc;
+        } else {
+            tmY = tmB;
+        }
+    }
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     static size_t configured_smem = 0;
     if (smem > configured_smem) {
@@ -407,7 +483,7 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
         configured_smem = 225 * 1024;
     }
     dim3 grid(gcb_cdiv(Cout, p.BN), gcb_cdiv(M, BM));
-    gemm_tc_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, p);
+    gemm_tc_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p);
     GCB_LAUNCH_CHECK();
     return GCB_OK;
 }

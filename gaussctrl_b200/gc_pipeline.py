@@ -39,6 +39,15 @@ def select_ref_indices(view_num: int, ref_view_num: int) -> List[int]:
     return [min(i, view_num - 1) for i in idx]
 
 
+def crossview_ref_frames(ref_view_num: int) -> tuple:
+    """Which rows of the reference block serve as K/V sources of the cross-view attention.  The reference hard-codes
+    frames 0,1,2,3 of each CFG half (utils.py:95-109): with R=4 those are the four reference views; with R=8 (BASELINE
+    cfg4) only the first four of the eight are sources - kept; with R<4 the reference reads chunk views as if they were
+    references, or raises IndexError at R=c=1 (SURVEY §8a gotcha 1) - here the K = R references that exist are used with
+    weights (1-coeff)/K (documented deviation)."""
+    return tuple(range(min(int(ref_view_num), 4)))
+
+
 def synthetic_prompt_embeds(prompts: Sequence[str], seq: int = 77, dim: int = 768) -> torch.Tensor:
     """Stand-in for the CLIP text encoder when no checkpoint is on disk: a deterministic N(0,1) embedding per prompt
     string.  (CLIP itself is outside the hot path: it runs once per `pipe()` call in the reference.)"""
@@ -162,12 +171,17 @@ class GaussCtrlPipeline(VanillaPipeline):
         emb = self.prompt_encoder([self.negative_prompts, self.positive_prompt])
         neg, pos = emb[0:1], emb[1:2]
         S, g = self.num_inference_steps, float(self.guidance_scale)
+        if g <= 1.0:
+            # diffusers does not double the batch for CFG then, and CrossViewAttnProcessor's `video_length = B // 2`
+            # (utils.py:94) silently mixes views: every shipped script uses g in {3, 5, 7.5} (SURVEY §8a gotcha 2)
+            raise ValueError(f"guidance_scale={g} <= 1: the cross-view attention layout needs classifier-free guidance")
         if self.config.edit_schedule == "reference":
             R = self.num_ref_views
             outs = []
             for i in range(0, V, self.chunk_size):
                 sel = list(self.ref_indices) + list(range(i, min(V, i + self.chunk_size)))
-                outs.append(self.engine.edit_reference_schedule(z_dev[sel], disparity[sel], pos, neg, S, g, R))
+                outs.append(self.engine.edit_reference_schedule(z_dev[sel], disparity[sel], pos, neg, S, g, R,
+                                                                ref_frames=crossview_ref_frames(R)))
             lat = torch.cat(outs)
             mine = list(range(V))
         else:
@@ -185,7 +199,7 @@ class GaussCtrlPipeline(VanillaPipeline):
                 mine = sorted(view_ids + (list(self.ref_indices) if rank == 0 else []))
             lat = self.engine.edit_refs_once(z_dev, disparity, self.ref_indices, pos, neg, S, g,
                                              view_batch=max(1, getattr(self, "view_batch", self.chunk_size)), view_ids=view_ids,
-                                             dist_ctx=dist_ctx)
+                                             dist_ctx=dist_ctx, ref_frames=crossview_ref_frames(self.num_ref_views))
         masks = uned = None
         if all("mask_image" in td[i] for i in mine):
             masks = torch.from_numpy(np.stack([np.asarray(td[i]["mask_image"], dtype=np.float32) for i in mine])).to(dev)

@@ -11,11 +11,12 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (GCB_ACT_GEGLU, GCB_ACT_NONE, GCB_ACT_SILU, GCB_ATTN_AUTO, GCB_GEMM_MMA_SYNC, GCB_GEMM_TCGEN05, check,
+from ._lib import (GCB_ACT_GEGLU, GCB_ACT_NONE, GCB_ACT_SILU, GCB_ATTN_AUTO, GCB_GEMM_MMA_SYNC, GCB_GEMM_TCGEN05,
+                   GCB_GEMM_TCGEN05_DIRECT, check,
                    lib)
 
 LAUNCHES = [0]  # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
-GEMM_LOG = None  # set to a list to record (B, H, W, Cin, Cout, ksize, act) of every conv2d call (profiling aid)
+GEMM_LOG = None  # set to a list to record (B, H, W, Cin, Cout, ksize, act, has_bias, has_rowvec, has_residual) per conv2d call
 
 _GEMM_IMPL = [GCB_GEMM_TCGEN05]
 _ATTN_IMPL = [GCB_ATTN_AUTO]
@@ -60,7 +61,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], ksize
     if residual is not None:
         assert residual.shape == y.shape and residual.is_contiguous()
     if GEMM_LOG is not None:
-        GEMM_LOG.append((B, H, W, Cin, Cout, ksize, act))
+        GEMM_LOG.append((B, H, W, Cin, Cout, ksize, act, bias is not None, rowvec is not None, residual is not None))
     check(lib.gcb_conv2d_nhwc_fwd(_p(x), _p(w), _p(bias), _p(rowvec, rowvec_off), rowvec_ld, _p(residual), _p(y), B, H, W,
                                   Cin, Cout, ksize, act, _GEMM_IMPL[0], _stream()))
     LAUNCHES[0] += 1

@@ -130,3 +130,12 @@ def test_pipeline_config_defaults_match_reference():
     c = GaussCtrlPipelineConfig()
     assert (c.render_rate, c.edit_prompt, c.reverse_prompt, c.langsam_obj, c.guidance_scale, c.num_inference_steps,
             c.chunk_size, c.ref_view_num, c.diffusion_ckpt) == (500, "", "", "", 5, 20, 5, 4, "CompVis/stable-diffusion-v1-4")
+
+
+def test_crossview_ref_frames_for_every_baseline_config():
+    """utils.py:95-109 gathers frames 0..3; R=8 keeps that (first four of eight), R<4 uses the references that exist."""
+    from gaussctrl_b200.gc_pipeline import crossview_ref_frames
+    assert crossview_ref_frames(4) == (0, 1, 2, 3)      # cfg2, cfg3, cfg5
+    assert crossview_ref_frames(8) == (0, 1, 2, 3)      # cfg4: refs 4..7 are batch rows only
+    assert crossview_ref_frames(1) == (0,)              # cfg1: the literal reference raises IndexError here
+    assert crossview_ref_frames(3) == (0, 1, 2)

@@ -62,7 +62,7 @@ GEMM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma_sync", "tcgen05_direct_epilogue"])
 @pytest.mark.parametrize("case", GEMM_CASES)
 def test_conv_gemm(ops, impl, case):
     B, H, W, Cin, Cout, k = case
@@ -79,7 +79,7 @@ def test_conv_gemm(ops, impl, case):
         ops.set_gemm_impl(0)
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma_sync", "tcgen05_direct_epilogue"])
 def test_conv_epilogues(ops, impl):
     ops.set_gemm_impl(impl)
     try:
@@ -97,6 +97,45 @@ def test_conv_epilogues(ops, impl):
         assert rel < 2e-3, (rel, mx)
     finally:
         ops.set_gemm_impl(0)
+
+
+@pytest.mark.parametrize("case", [
+    # B, H, W, Cin, Cout, k, act, residual, rowvec
+    (1, 1, 154, 768, 2304, 1, 0, False, False),   # CLIP qkv: ragged M (two tiles, 26 valid rows in the second)
+    (1, 1, 154, 3072, 768, 1, 0, True, False),    # CLIP fc2 + residual, K = 3072
+    (2, 64, 64, 320, 320, 1, 0, True, False),     # BN = 160: two staged 64-column groups + one 32-column direct chunk
+    (2, 64, 64, 320, 72, 1, 0, False, False),     # N tail: second 64-column group is partial -> direct stores
+    (2, 64, 64, 320, 64, 1, 1, False, True),      # exactly one staged group, SiLU + per-image vector
+    (3, 32, 32, 640, 640, 3, 1, True, True),      # conv3x3, every epilogue term
+    (2, 32, 32, 640, 5120, 1, 2, False, False),   # GEGLU, BN = 256
+    (1, 16, 16, 1280, 10240, 1, 2, False, False),  # GEGLU at the 16x16 level
+    (5, 64, 64, 320, 256, 1, 0, True, False),     # BN = 256: four staged groups per warp (buffer reuse + wait_group)
+])
+def test_tma_store_epilogue_equals_direct_epilogue(ops, case):
+    """The staged TMA-store epilogue (default) and the round-1 per-thread row stores write bit-identical tensors:
+    same fp32 accumulators, same epilogue arithmetic, only the path to HBM differs."""
+    B, H, W, Cin, Cout, k, act, has_res, has_rv = case
+    x = _rand((B, H, W, Cin), 11)
+    w = _rand((Cout, k * k * Cin), 12, scale=1.0 / math.sqrt(k * k * Cin))
+    bias = _rand((Cout,), 13)
+    co = Cout // 2 if act == 2 else Cout
+    res = _rand((B, H, W, co), 14) if has_res else None
+    rv = _rand((B, Cout), 15) if has_rv else None
+    outs = []
+    try:
+        for impl in (0, 2):
+            ops.set_gemm_impl(impl)
+            y = torch.full((B, H, W, co), float("nan"), dtype=torch.float16, device="cuda")  # every element must be written
+            ops.conv2d(x, w, bias, k, act=act, rowvec=rv, rowvec_ld=Cout if has_rv else 0, residual=res, out=y)
+            torch.cuda.synchronize()
+            outs.append(y)
+    finally:
+        ops.set_gemm_impl(0)
+    assert not torch.isnan(outs[0].float()).any() and not torch.isnan(outs[1].float()).any()
+    assert torch.equal(outs[0], outs[1])
+    if act != 2:
+        rel, mx = _relerr(outs[0], _conv_ref(x, w, bias, k, rowvec=rv, residual=res, act=act))
+        assert rel < 2e-3, (rel, mx)
 
 
 @pytest.mark.parametrize("C", [320, 640, 1280])
