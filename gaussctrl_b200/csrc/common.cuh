@@ -60,18 +60,31 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// MUFU approximations (1 instruction each, <= 2 ulp): the IEEE-rounded forms (`/`, __frcp_rn, __expf's denormal
+// fix-ups) cost 8-20 extra instructions per element in the GEMM / GroupNorm epilogues, which are issue-bound.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// x * sigmoid(x).  x -> -large: ex2 -> inf, rcp -> 0, result -0 (the limit); x -> +large: ex2 -> 0, result x.
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
 // exact (erf) GELU, x * Phi(x), with erfc from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output
-// rounding): ~11 instructions instead of erff's ~30 - the GEGLU GEMM epilogue is issue-bound on this function.
+// rounding): ~17 instructions (2 MUFU) instead of erff's ~30 - the GEGLU GEMM epilogue is issue-bound on this function.
 // The negative branch uses erfc directly (no 1 - (1 - e) cancellation).
 __device__ __forceinline__ float gelu_erf_f(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float e = p * t * __expf(-z * z);  // erfc(z), z >= 0
+    const float e = p * t * ex2_approx(z * z * -1.4426950408889634f);  // erfc(z), z >= 0
     return 0.5f * x * (x >= 0.f ? 2.f - e : e);
 }
 

@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         }
     } else {
         // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+        // Software-pipelined: the tcgen05.ld of the NEXT column chunk is in flight while the current chunk is
+        // converted, so the TMEM read latency is exposed once per tile instead of once per chunk.
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const long long m = (long long)m_tile * BM + row;
@@ -166,12 +168,38 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const uint32_t stage_buf = smem_base + (uint32_t)q * 8192u;
         const int y_row0 = m_tile * BM + q * 32;
         int n_pairs = 0;                                        // staged 64-column groups so far (buffer = n_pairs & 1)
+        auto add8 = [](float* v, const uint4& u) {
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_half2(w[t]);
+                v[t * 2] += f.x;
+                v[t * 2 + 1] += f.y;
+            }
+        };
+        // a 64-column group is complete in the staging buffer: one bulk store, then switch buffers
+        auto flush_group = [&](int col0) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (issuer) {
+                tma_store_2d(&tmY, stage_buf + (uint32_t)((n_pairs & 1) * 4096), col0, y_row0);
+                tma_store_commit();
+            }
+            ++n_pairs;
+        };
+        // before the first write into a staging buffer: the bulk store that last used it must have read it
+        auto acquire_buffer = [&]() {
+            if (n_pairs >= 2) {
+                if (issuer) tma_store_wait_read<1>();
+                __syncwarp();
+            }
+        };
         if (p.act != GCB_ACT_GEGLU) {
             const int nchunks = p.BN / 32;
             const int ncol0 = n_tile * p.BN;
             const __half* res_row = p.residual ? p.residual + m * p.ldy : nullptr;
             const __half* rv_row = p.rowvec ? p.rowvec + (long long)img * p.rowvec_ld : nullptr;
-            // software pipeline: the residual of chunk c+1 is in flight while chunk c is converted and stored
+            // the residual of chunk c+1 is in flight while chunk c is converted and stored
             uint4 res_cur[4], res_nxt[4];
             auto load_res = [&](int c, uint4 (&dst)[4]) {
                 const int n0 = ncol0 + c * 32;
@@ -181,60 +209,30 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                     for (int g = 0; g < 4; ++g) dst[g] = rp[g];
                 }
             };
-            load_res(0, res_cur);
-            mbar_wait(smem_u32(&tmem_full_bar), 0);
-            tc_fence_after();
-            if (p.epi) fence_proxy_async_smem();  // generic writes below follow the TMA (async proxy) fills of the ring
             bool pair_staged = false;
-            for (int c = 0; c < nchunks; ++c) {
+            auto chunk = [&](const uint32_t (&r)[32], int c) {
                 const int n0 = ncol0 + c * 32;
                 if ((c & 1) == 0) {
                     pair_staged = p.epi && c + 1 < nchunks && n0 + 64 <= p.N;
-                    if (pair_staged && n_pairs >= 2) {  // the store that last used this buffer must have read it
-                        if (issuer) tma_store_wait_read<1>();
-                        __syncwarp();
-                    }
+                    if (pair_staged) acquire_buffer();
                 }
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
                 if (c + 1 < nchunks) load_res(c + 1, res_nxt);
                 const bool full = n0 + 32 <= p.N;
-                uint4 bv[4], rvv[4];
-                if (full) {
-                    if (p.bias) {
-                        const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) bv[g] = bp[g];
-                    }
-                    if (rv_row) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(rv_row + n0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) rvv[g] = rp[g];
-                    }
-                }
-                tc_wait_ld();
                 if ((row_ok || pair_staged) && n0 < p.N) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     __half* yp = p.y + m * p.ldy + n0;
                     if (full) {
-                        auto add8 = [&](const uint4& u, int g) {
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float2 f = unpack_half2(w[t]);
-                                v[g * 8 + t * 2] += f.x;
-                                v[g * 8 + t * 2 + 1] += f.y;
-                            }
-                        };
                         if (p.bias) {
+                            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + n0);
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) add8(bv[g], g);
+                            for (int g = 0; g < 4; ++g) add8(v + g * 8, bp[g]);
                         }
                         if (rv_row) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(rv_row + n0);
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) add8(rvv[g], g);
+                            for (int g = 0; g < 4; ++g) add8(v + g * 8, rp[g]);
                         }
                         if (p.act == GCB_ACT_SILU) {
 #pragma unroll
@@ -242,7 +240,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                         }
                         if (res_row && row_ok) {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) add8(res_cur[g], g);
+                            for (int g = 0; g < 4; ++g) add8(v + g * 8, res_cur[g]);
                         }
                         if (pair_staged) {
                             stage_row_half(stage_buf + (uint32_t)((n_pairs & 1) * 4096), lane, c & 1, v);
@@ -273,71 +271,85 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                         }
                     }
                 }
-                if (pair_staged && (c & 1)) {  // both halves of the 32 x 64 tile are in smem: one bulk store
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (issuer) {
-                        tma_store_2d(&tmY, stage_buf + (uint32_t)((n_pairs & 1) * 4096), n0 - 32, y_row0);
-                        tma_store_commit();
-                    }
-                    ++n_pairs;
-                }
+                if (pair_staged && (c & 1)) flush_group(n0 - 32);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) res_cur[g] = res_nxt[g];
-            }
-        } else {
-            // GEGLU: tile columns [0, BN/2) = value, [BN/2, BN) = gate; output width N/2
+            };
+            load_res(0, res_cur);
             mbar_wait(smem_u32(&tmem_full_bar), 0);
             tc_fence_after();
+            if (p.epi) fence_proxy_async_smem();  // generic writes below follow the TMA (async proxy) fills of the ring
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32b_x32(taddr, ra);
+            for (int c = 0; c < nchunks; c += 2) {
+                tc_wait_ld();  // ra = chunk c
+                const bool has2 = c + 1 < nchunks;
+                if (has2) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), rb);
+                chunk(ra, c);
+                if (has2) {
+                    tc_wait_ld();  // rb = chunk c+1
+                    if (c + 2 < nchunks) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 2) * 32), ra);
+                    chunk(rb, c + 1);
+                }
+            }
+        } else {
+            // GEGLU: tile columns [0, BN/2) = value, [BN/2, BN) = gate; output width N/2.  Steps of 16 output columns
+            // (16 value + 16 gate accumulators), double-buffered; four steps fill one 64-column staging group.
+            // BN is 128 or 256 and N % BN == 0 (gcb_geglu_tile_n), so every group is full.
             const int half_bn = p.BN / 2;
-            const int n_out = p.N / 2;
+            const int nsteps = half_bn / 16;                    // 4 or 8
+            const int t0 = n_tile * p.BN;                       // packed-row offset of this tile (bias index)
+            const int ocol0 = n_tile * half_bn;                 // first output column of this tile
+            auto step = [&](const uint32_t (&rv)[16], const uint32_t (&rg)[16], int s) {
+                if (p.epi && (s & 3) == 0) acquire_buffer();
+                float val[16], gate[16], o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    val[j] = __uint_as_float(rv[j]);
+                    gate[j] = __uint_as_float(rg[j]);
+                }
+                if (p.bias) {
+                    const uint4* bvp = reinterpret_cast<const uint4*>(p.bias + t0 + s * 16);
+                    const uint4* bgp = reinterpret_cast<const uint4*>(p.bias + t0 + half_bn + s * 16);
+                    add8(val, bvp[0]);
+                    add8(val + 8, bvp[1]);
+                    add8(gate, bgp[0]);
+                    add8(gate + 8, bgp[1]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = val[j] * gelu_erf_f(gate[j]);
+                const uint32_t h0 = pack_half2(o[0], o[1]), h1 = pack_half2(o[2], o[3]), h2 = pack_half2(o[4], o[5]),
+                               h3 = pack_half2(o[6], o[7]), h4 = pack_half2(o[8], o[9]), h5 = pack_half2(o[10], o[11]),
+                               h6 = pack_half2(o[12], o[13]), h7 = pack_half2(o[14], o[15]);
+                if (p.epi) {
+                    const uint32_t buf = stage_buf + (uint32_t)((n_pairs & 1) * 4096) + (uint32_t)(lane * 128);
+                    const int j0 = (s & 3) * 2;                 // 16-byte piece of the 128-byte row
+                    st_shared_v4(buf + (uint32_t)(((j0) ^ (lane & 7)) << 4), h0, h1, h2, h3);
+                    st_shared_v4(buf + (uint32_t)(((j0 + 1) ^ (lane & 7)) << 4), h4, h5, h6, h7);
+                    if ((s & 3) == 3) flush_group(ocol0 + (s - 3) * 16);
+                } else if (row_ok) {
+                    uint4* op = reinterpret_cast<uint4*>(p.y + m * p.ldy + ocol0 + s * 16);
+                    op[0] = make_uint4(h0, h1, h2, h3);
+                    op[1] = make_uint4(h4, h5, h6, h7);
+                }
+            };
+            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            tc_fence_after();
             if (p.epi) fence_proxy_async_smem();
-            for (int c = 0; c < half_bn / 32; ++c) {
-                if (p.epi && (c & 1) == 0 && n_pairs >= 2) {
-                    if (issuer) tma_store_wait_read<1>();
-                    __syncwarp();
+            uint32_t va[16], ga[16], vb[16], gb[16];
+            tmem_ld_32x32b_x16(taddr, va);
+            tmem_ld_32x32b_x16(taddr + (uint32_t)half_bn, ga);
+            for (int s = 0; s < nsteps; s += 2) {
+                tc_wait_ld();  // va / ga = step s
+                tmem_ld_32x32b_x16(taddr + (uint32_t)((s + 1) * 16), vb);
+                tmem_ld_32x32b_x16(taddr + (uint32_t)(half_bn + (s + 1) * 16), gb);
+                step(va, ga, s);
+                tc_wait_ld();  // vb / gb = step s+1
+                if (s + 2 < nsteps) {
+                    tmem_ld_32x32b_x16(taddr + (uint32_t)((s + 2) * 16), va);
+                    tmem_ld_32x32b_x16(taddr + (uint32_t)(half_bn + (s + 2) * 16), ga);
                 }
-                uint32_t rv[32], rg[32];
-                tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), rv);
-                tmem_ld_32x32b_x32(taddr + (uint32_t)(half_bn + c * 32), rg);
-                tc_wait_ld();
-                const int t0 = n_tile * p.BN;                 // packed-row offset of this tile
-                const int o0 = n_tile * half_bn + c * 32;     // output column
-                if ((!row_ok && !p.epi) || o0 >= n_out) continue;
-                float o[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float val = __uint_as_float(rv[j]);
-                    float gate = __uint_as_float(rg[j]);
-                    if (p.bias) {
-                        val += __half2float(p.bias[t0 + c * 32 + j]);
-                        gate += __half2float(p.bias[t0 + half_bn + c * 32 + j]);
-                    }
-                    o[j] = val * gelu_erf_f(gate);
-                }
-                if (p.epi) {  // half_bn / 32 is even and n_out % 64 == 0: every pair is a full 32 x 64 tile
-                    stage_row_half(stage_buf + (uint32_t)((n_pairs & 1) * 4096), lane, c & 1, o);
-                    if (c & 1) {
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (issuer) {
-                            tma_store_2d(&tmY, stage_buf + (uint32_t)((n_pairs & 1) * 4096), o0 - 32, y_row0);
-                            tma_store_commit();
-                        }
-                        ++n_pairs;
-                    }
-                    continue;
-                }
-                uint4* op = reinterpret_cast<uint4*>(p.y + m * p.ldy + o0);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 u;
-                    u.x = pack_half2(o[g * 8 + 0], o[g * 8 + 1]);
-                    u.y = pack_half2(o[g * 8 + 2], o[g * 8 + 3]);
-                    u.z = pack_half2(o[g * 8 + 4], o[g * 8 + 5]);
-                    u.w = pack_half2(o[g * 8 + 6], o[g * 8 + 7]);
-                    op[g] = u;
-                }
+                step(vb, gb, s + 1);
             }
         }
         if (p.epi && issuer) tma_store_wait_read<0>();  // smem must outlive the bulk stores that read it
