@@ -279,10 +279,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         };
         issue_qk(0, 0);
         issue_qk(1, 0);
+        // Both S(i+1) products go out as soon as the slots have read S(i) (the start of their tile i), a whole tile
+        // ahead of when they are needed.  With qk(1, i+1) queued behind pv(0, i) (the round-1 order) slot 1 spent ~10 %
+        // of its time spinning on s_full (ncu source view, profiles/r1i_attn_source_summary.md): pv(0, i) blocks this
+        // warp until slot 0 has finished its exponentials.
         for (int i = 0; i < T; ++i) {
-            if (i + 1 < T) issue_qk(0, i + 1);
+            if (i + 1 < T) {
+                issue_qk(0, i + 1);
+                issue_qk(1, i + 1);
+            }
             issue_pv(0, i);
-            if (i + 1 < T) issue_qk(1, i + 1);
             issue_pv(1, i);
         }
     } else {

@@ -388,7 +388,15 @@ int choose_bn(int M, int N, int act) {
 
 }  // namespace
 
-extern "C" int gcb_geglu_tile_n(int Cout) { return ((Cout / 2) % 128 == 0) ? 256 : 128; }
+extern "C" int gcb_geglu_tile_n(int Cout) {
+    static int forced = -1;  // GCB_GEGLU_BN=128: tuning knob (the weight packing follows this function, so it is consistent)
+    if (forced < 0) {
+        const char* e = getenv("GCB_GEGLU_BN");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 128) return 128;
+    return ((Cout / 2) % 128 == 0) ? 256 : 128;
+}
 
 // perm[r_packed] = source row in the diffusers [value(4C) ; gate(4C)] projection
 extern "C" int gcb_geglu_pack_rows(int Cout, int32_t* h_perm) {
