@@ -28,6 +28,10 @@ constexpr int MAX_SRC = 8;
 constexpr int BM = 128;  // query rows per slot
 constexpr int STAGES = 4;
 constexpr float RESCALE_THRESHOLD = 8.f;
+#ifndef GCB_ATTN_LAG
+#define GCB_ATTN_LAG 0
+#endif
+constexpr int ATTN_LAG = GCB_ATTN_LAG;  // 0 = off, 1 = slot 0 signals after its row max, 2 = after half of its exponentials
 
 template <int D_>
 struct Cfg;
@@ -79,6 +83,7 @@ struct __align__(1024) Smem {
     uint64_t q_full, q_ready;
     uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
     uint64_t s_full[2], s_free[2], p_ready[2], p_free[2], o_free[2];
+    uint64_t lag_bar;
     uint32_t tmem_base;
 };
 
@@ -108,6 +113,20 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
     uint32_t y;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
     return y;
+}
+// mbarrier arrive whose address carries a (zero) data dependency on `dep`, so that neither nvcc nor ptxas can move it
+// ahead of the instruction that produces `dep`:  (dep >> 31) & (~dep >> 31) == 0 for every dep.
+__device__ __forceinline__ void lag_arrive(uint32_t bar, uint32_t dep) {
+    asm volatile(
+        "{\n\t.reg .b32 a, b;\n\t"
+        "shr.u32 a, %1, 31;\n\t"
+        "not.b32 b, %1;\n\t"
+        "shr.u32 b, b, 31;\n\t"
+        "and.b32 a, a, b;\n\t"
+        "add.u32 a, a, %0;\n\t"
+        "mbarrier.arrive.shared::cta.b64 _, [a];\n\t}"
+        ::"r"(bar), "r"(dep)
+        : "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
@@ -178,6 +197,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(smem_u32(&sm.p_free[t]), 1);
             mbar_init(smem_u32(&sm.o_free[t]), 128);
         }
+        mbar_init(smem_u32(&sm.lag_bar), 128);
         mbar_fence_init();
     }
     if (warp == 9) {
@@ -279,16 +299,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         };
         issue_qk(0, 0);
         issue_qk(1, 0);
-        // Both S(i+1) products go out as soon as the slots have read S(i) (the start of their tile i), a whole tile
-        // ahead of when they are needed.  With qk(1, i+1) queued behind pv(0, i) (the round-1 order) slot 1 spent ~10 %
-        // of its time spinning on s_full (ncu source view, profiles/r1i_attn_source_summary.md): pv(0, i) blocks this
-        // warp until slot 0 has finished its exponentials.
+        // Issue order.  qk(1, i+1) sits behind pv(0, i), which blocks until slot 0 has finished the exponentials of tile
+        // i: slot 1 therefore starts every tile a fixed lag after slot 0.  That coupling is deliberate - with both QK^T
+        // products issued ahead of the PVs (tried in r1j) the slots fall into step, their non-MUFU phases coincide and
+        // the kernel is 6 % SLOWER (518 -> 486 TFLOP/s).  GCB_ATTN_LAG > 0 lengthens the lag instead: qk(1, i+1)
+        // additionally waits until slot 0 has reached a given point of tile i+1 (lag_bar).  Also measured (r1k) and
+        // rejected: 513 -> 427 (signal after the row max) / 434 TFLOP/s (after half of the exponentials) at d=40,
+        // 729 -> 535 at d=80.  The round-1 order below is the measured optimum of the three; kept at 0.
+        if (ATTN_LAG) mbar_wait(smem_u32(&sm.lag_bar), 0);
         for (int i = 0; i < T; ++i) {
+            if (i + 1 < T) issue_qk(0, i + 1);
+            issue_pv(0, i);
             if (i + 1 < T) {
-                issue_qk(0, i + 1);
+                if (ATTN_LAG) mbar_wait(smem_u32(&sm.lag_bar), ((uint32_t)(i + 1)) & 1u);
                 issue_qk(1, i + 1);
             }
-            issue_pv(0, i);
             issue_pv(1, i);
         }
     } else {
@@ -368,6 +393,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 // p = 2^(s*scale - m), kept in registers as packed halves (reusing the score registers) ...
                 const float negm = -m;
+                if (ATTN_LAG == 1 && t == 0) lag_arrive(smem_u32(&sm.lag_bar), __float_as_uint(mx));
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 const bool sum_here = !p.l_from_o;
 #pragma unroll
@@ -404,6 +430,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     sr[e] = cvt_f16x2(p0, p1);
                     sr[e + 1] = cvt_f16x2(p2, p3);
                 }
+                if (ATTN_LAG == 2 && t == 0) lag_arrive(smem_u32(&sm.lag_bar), sr[BN / 4 - 1]);
                 l += (l0 + l1) + (l2 + l3);
                 // ... so that the wait for P(i-1) to be consumed by its P V product overlaps the exponentials
                 if (!waited) {
