@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--views", type=int, default=40, help="views per GPU (bear-like scene: 40)")
     ap.add_argument("--gaussians", type=int, default=1_000_000)
     ap.add_argument("--ddim-steps", type=int, default=S_STEPS)
-    ap.add_argument("--view-batch", type=int, default=12,
+    ap.add_argument("--view-batch", type=int, default=40,
                     help="views denoised per launch in the refs-once schedule (results do not depend on it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -335,10 +335,15 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        Bq, C = 2 * args.view_batch, ATTN_C
+        # the launch shape of the view batches: the engine splits the non-reference views of this rank into the fewest
+        # equal batches of at most --view-batch views (engine.edit_refs_once)
+        n_nonref = len([v for v in (view_ids if view_ids is not None else range(V)) if v not in set(pipe.ref_indices)])
+        n_b = max(1, -(-n_nonref // max(1, args.view_batch)))
+        vb_eff = max(1, -(-n_nonref // n_b))
+        Bq, C = 2 * vb_eff, ATTN_C
         qkv = torch.randn((Bq, ATTN_N, 3 * C), device=dev).half()
         refkv = torch.randn((2 * REFS, ATTN_N, 3 * C), device=dev).half()
-        vb = args.view_batch
+        vb = vb_eff
         rows = [[h * vb + f] + [-(h * REFS + r) - 1 for r in range(4)] for h in range(2) for f in range(vb)]
         idx = torch.tensor(rows, dtype=torch.int32, device=dev)
         w = [0.6, 0.1, 0.1, 0.1, 0.1]
@@ -360,8 +365,9 @@ def main():
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of the same shape
             tj = json.load(open(os.path.join(REPO, "profiles", "attn_ncu_traffic.json")))
-            if vb == 12:
-                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            ent = tj.get("by_rows", {}).get(str(Bq))   # captures are per launch shape (B = CFG rows of a view batch)
+            if ent:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         except Exception:
             pass
         roof = {"bound": "tensor", "kernel": "multi-source cross-view attention N=4096 d=40 (5 K/V sources)",
@@ -392,7 +398,8 @@ def main():
                                      "note": "CUDA events around GaussCtrlModel.get_outputs_for_camera (host syncs of "
                                              "the binning included); roofline bound = HBM"},
                           "schedule": "refs_once (reference views denoised once per DDIM step, K/V recorded)",
-                          "view_batch": args.view_batch, "breakdown": breakdown,
+                          "view_batch": args.view_batch, "views_per_launch": vb_eff if rank == 0 else None,
+                          "breakdown": breakdown,
                           "render_reverse_ms": stage_a_ms, "finetune": finetune,
                           "views_per_s_stage_a_plus_b": (V / ((stage_a_ms + ms_per_step) / 1e3)) if stage_a_ms else None,
                           "views_total": V,

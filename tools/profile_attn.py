@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gaussctrl_b200 import ops
-Bq, N, C, R = 24, 4096, 320, 4
+Bq, N, C, R = int(os.environ.get("GCB_PROFILE_BQ", "24")), 4096, 320, 4
 qkv = torch.randn((Bq, N, 3 * C), device="cuda").half()
 refkv = torch.randn((2 * R, N, 3 * C), device="cuda").half()
 rows = [[h * (Bq // 2) + f] + [-(h * R + r) - 1 for r in range(4)] for h in range(2) for f in range(Bq // 2)]
