@@ -1,6 +1,9 @@
 // Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (sm_100a):
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (kind::f16) -> TMEM accumulator
-//   -> tcgen05.ld epilogue (bias / per-image vector / residual / SiLU / GEGLU) -> fp16 store.
+//   -> software-pipelined tcgen05.ld epilogue (bias / per-image vector / residual / SiLU / GEGLU) -> 32x64 fp16 tiles
+//   staged in the (by then free) operand ring -> cp.async.bulk.tensor store (TMA), clipped at the tensor bounds.
+// Two CTAs are resident per SM (<= 110 KB of ring each, <= 256 TMEM columns each, 167 registers x 192 threads), so the
+// epilogue of one tile overlaps the main loop of another.  Measured per layer shape: profiles/r1i_gemm_table.txt.
 //
 // y[M, Cout] = act( im2col(x)[M, taps*Cin] * w[Cout, taps*Cin]^T + bias + rowvec[b] ) + residual
 //
