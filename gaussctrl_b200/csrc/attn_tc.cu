@@ -22,6 +22,8 @@
 #include "../../include/gaussctrl_b200.h"
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace {
 
 constexpr int MAX_SRC = 8;
@@ -31,6 +33,20 @@ constexpr float RESCALE_THRESHOLD = 8.f;
 #ifndef GCB_ATTN_LAG
 #define GCB_ATTN_LAG 0
 #endif
+#ifndef GCB_ATTN_SPLIT_LD
+#define GCB_ATTN_SPLIT_LD 0
+#endif
+#ifndef GCB_ATTN_SPLIT_ST
+#define GCB_ATTN_SPLIT_ST 1
+#endif
+// The non-MUFU part of a tile (BN = 128 only; profiles/r1i_attn_source_summary.md), A/B in one process with
+// tools/ab_attn_libs.py at B=24, N=4096, d=40 (profiles/r1o_ab_attn_split.txt; outputs bit-identical in all four builds):
+//   SPLIT_ST (ON): the first 64 packed probabilities are stored (tcgen05.st) after half of the exponentials; the p_free
+//             spin in between also splits the basic block, so ptxas can no longer sink all 64 packs behind the last
+//             ex2: 487.5 -> 538.1 TFLOP/s (+10 %).
+//   SPLIT_LD (off): the second half of S still loading from TMEM while the row max of the first half is taken:
+//             484.7 TFLOP/s alone, 535.7 with SPLIT_ST - no gain, the TMEM-load latency is not what the max phase waits on.
+constexpr bool ATTN_SPLIT_LD = GCB_ATTN_SPLIT_LD != 0, ATTN_SPLIT_ST = GCB_ATTN_SPLIT_ST != 0;
 constexpr int ATTN_LAG = GCB_ATTN_LAG;  // 0 = off, 1 = slot 0 signals after its row max, 2 = after half of its exponentials
 
 template <int D_>
@@ -346,6 +362,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 uint32_t sr[BN];
                 tmem_ld32_into<0>(s_t, sr);
                 tmem_ld32_into<32>(s_t + 32, sr);
+                float mxa, mxb, mxc, mxd;
+                if (ATTN_SPLIT_LD && BN == 128) {
+                    tc_wait_ld();  // first 64 columns are in registers
+                    tmem_ld32_into<(BN == 128 ? 64 : 0)>(s_t + 64, sr);
+                    tmem_ld32_into<(BN == 128 ? 96 : 0)>(s_t + 96, sr);
+                    mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
+                    mxd = __uint_as_float(sr[3]);
+#pragma unroll
+                    for (int e = 4; e < 64; e += 8) {
+                        mxa = fmax3(mxa, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
+                        mxb = fmax3(mxb, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
+                        if (e + 4 < 64) {
+                            mxc = fmax3(mxc, __uint_as_float(sr[e + 4]), __uint_as_float(sr[e + 5]));
+                            mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
+                        }
+                    }
+                    tc_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&sm.s_free[t]));
+#pragma unroll
+                    for (int e = 64; e < BN; e += 8) {
+                        mxa = fmax3(mxa, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
+                        mxb = fmax3(mxb, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
+                        mxc = fmax3(mxc, __uint_as_float(sr[e + 4]), __uint_as_float(sr[e + 5]));
+                        mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
+                    }
+                } else {
                 if (BN == 128) {
                     tmem_ld32_into<(BN == 128 ? 64 : 0)>(s_t + 64, sr);
                     tmem_ld32_into<(BN == 128 ? 96 : 0)>(s_t + 96, sr);
@@ -354,8 +397,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sm.s_free[t]));
                 // tile max (raw scores; scale > 0 so max commutes with scaling): four independent chains
-                float mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
-                      mxd = __uint_as_float(sr[3]);
+                mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
+                mxd = __uint_as_float(sr[3]);
 #pragma unroll
                 for (int e = 4; e < BN; e += 8) {
                     mxa = fmax3(mxa, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
@@ -364,6 +407,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         mxc = fmax3(mxc, __uint_as_float(sr[e + 4]), __uint_as_float(sr[e + 5]));
                         mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
                     }
+                }
                 }
                 const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)) * p.scale_log2;
                 bool waited = (i == 0);
@@ -396,8 +440,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (ATTN_LAG == 1 && t == 0) lag_arrive(smem_u32(&sm.lag_bar), __float_as_uint(mx));
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 const bool sum_here = !p.l_from_o;
+                auto exp_block = [&](auto e_begin, auto e_end) {
 #pragma unroll
-                for (int e = 0; e < BN / 2; e += 2) {
+                for (int e = decltype(e_begin)::value; e < decltype(e_end)::value; e += 2) {
                     const float x0 = fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm);
                     const float x1 = fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm);
                     const float x2 = fmaf(__uint_as_float(sr[2 * e + 2]), p.scale_log2, negm);
@@ -430,6 +475,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     sr[e] = cvt_f16x2(p0, p1);
                     sr[e + 1] = cvt_f16x2(p2, p3);
                 }
+                };
+                using std::integral_constant;
+                if (ATTN_SPLIT_ST && BN == 128) {
+                    exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 4>{});   // keys 0..63
+                    if (!waited) {
+                        mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
+                        tc_fence_after();
+                    }
+                    tmem_st32_from<0>(p_t, sr);                                                   // packed pairs 0..31
+                    exp_block(integral_constant<int, BN / 4>{}, integral_constant<int, BN / 2>{});  // keys 64..127
+                    l += (l0 + l1) + (l2 + l3);
+                    tmem_st32_from<(BN == 128 ? 32 : 0)>(p_t + 32, sr);
+                } else {
+                exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 2>{});
                 if (ATTN_LAG == 2 && t == 0) lag_arrive(smem_u32(&sm.lag_bar), sr[BN / 4 - 1]);
                 l += (l0 + l1) + (l2 + l3);
                 // ... so that the wait for P(i-1) to be consumed by its P V product overlaps the exponentials
@@ -440,6 +499,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 // A operand of P V in TMEM: lane = query row, column e = keys (2e, 2e+1) packed
                 tmem_st32_from<0>(p_t, sr);
                 if (BN == 128) tmem_st32_from<(BN == 128 ? 32 : 0)>(p_t + 32, sr);
+                }
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sm.p_ready[t]));
