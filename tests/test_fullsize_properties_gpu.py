@@ -1,0 +1,181 @@
+"""Parity at BASELINE.json's FULL sizes (configs[1]: 1 M Gaussians, 512x512 views, 64x64 latents = 4096 tokens), where
+the CPU oracle would need minutes to hours: size-independent properties of the domain instead of element-wise
+comparison - convexity and linearity of attention in V, exact power-of-two homogeneity and an independent second
+kernel for the convolutions, sortedness / multiplicity checksums of the tile binning, idempotence and range of the
+render.  (Element-wise parity against the oracle at small sizes: test_kernels_gpu.py, test_raster_gpu.py.)"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gaussctrl_b200 import ops as _ops
+    return _ops
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).half().cuda()
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _assert_exactly_doubled(y2, y):
+    """y2 == 2 * y bit for bit wherever the fp16 result is a normal number (scaling by two commutes with rounding
+    there); in the subnormal range the spacing is constant, so only |y2 - 2 y| <= one subnormal step is guaranteed."""
+    y2, y = y2.float(), y.float()
+    normal = y.abs() >= 2.0 ** -13
+    assert torch.equal(y2[normal], y[normal] * 2)
+    assert (y2[~normal] - y[~normal] * 2).abs().max().item() <= 2.0 ** -23 if (~normal).any() else True
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("N,d", [(4096, 40), (1024, 80)])
+def test_crossview_attention_properties_at_full_size(ops, N, d):
+    """Cross-view attention of one view batch at the bench's layer shapes (self + 4 cached reference sources)."""
+    heads, Bv, R = 8, 3, 4
+    C = heads * d
+    qkv = _rand((2 * Bv, N, 3 * C), 1)
+    ref = _rand((2 * R, N, 3 * C), 2)
+    rows = [[h * Bv + f] + [-(h * R + r) - 1 for r in range(4)] for h in range(2) for f in range(Bv)]
+    idx = torch.tensor(rows, dtype=torch.int32).cuda()
+    w = [0.6, 0.1, 0.1, 0.1, 0.1]
+
+    def attend(qkv_, ref_, idx_=idx, w_=w, B=2 * Bv):
+        return ops.attention(qkv_, 0, 3 * C, qkv_, C, 2 * C, 3 * C, ref_, C, 2 * C, 3 * C, B, N, N, heads, d, idx_, w_)
+
+    out = attend(qkv, ref)
+    assert torch.isfinite(out.float()).all()
+    # (1) convexity: with every value row equal to one vector c, each softmax average returns c, and the source weights
+    #     sum to 1 -> out == c up to the fp16 rounding of the probabilities and of the output
+    c = _rand((C,), 3)
+    qkv_c, ref_c = qkv.clone(), ref.clone()
+    qkv_c[..., 2 * C:] = c
+    ref_c[..., 2 * C:] = c
+    out_c = attend(qkv_c, ref_c)
+    assert (out_c.float() - c.float()).abs().max().item() < 4e-3 * max(1.0, c.float().abs().max().item())
+    # (2) linearity in V (the probabilities do not depend on V): out(V1) + out(V2) == out(V1 + V2)
+    qkv_2, ref_2 = qkv.clone(), ref.clone()
+    qkv_2[..., 2 * C:] = _rand((2 * Bv, N, C), 4)
+    ref_2[..., 2 * C:] = _rand((2 * R, N, C), 5)
+    qkv_s, ref_s = qkv.clone(), ref.clone()
+    qkv_s[..., 2 * C:] = (qkv[..., 2 * C:].float() + qkv_2[..., 2 * C:].float()).half()
+    ref_s[..., 2 * C:] = (ref[..., 2 * C:].float() + ref_2[..., 2 * C:].float()).half()
+    lin = _rel(attend(qkv_s, ref_s), out.float() + attend(qkv_2, ref_2).float())
+    assert lin < 5e-3, lin   # three fp16-rounded outputs and the fp16 rounding of V1 + V2
+    # (3) batch invariance: two of the six rows alone (one per CFG half) give bit-identical rows
+    sub = qkv[[0, Bv]].contiguous()
+    rows_sub = [[h] + [-(h * R + r) - 1 for r in range(4)] for h in range(2)]
+    out_sub = attend(sub, ref, torch.tensor(rows_sub, dtype=torch.int32).cuda(), w, 2)
+    assert torch.equal(out_sub, out[[0, Bv]])
+    # (4) a source listed twice with half the weight each == the source once (power-of-two scaling is exact in fp32)
+    rows_1 = [[-(h * R) - 1] for h in range(2) for _ in range(Bv)]
+    rows_2 = [[-(h * R) - 1, -(h * R) - 1] for h in range(2) for _ in range(Bv)]
+    once = attend(qkv, ref, torch.tensor(rows_1, dtype=torch.int32).cuda(), [1.0])
+    twice = attend(qkv, ref, torch.tensor(rows_2, dtype=torch.int32).cuda(), [0.5, 0.5])
+    assert torch.equal(once, twice)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM / conv
+def test_conv_gemm_properties_at_full_size(ops):
+    """The largest 3x3 convolution of a view batch (24 CFG rows x 64x64 x 320 -> 320, M = 98 304, K = 2 880):
+    two independent kernels (tcgen05 / TMA vs mma.sync) agree, and scaling the input by 2 scales the output by
+    exactly 2 (fp32 accumulation and one fp16 rounding commute with a power of two)."""
+    B, H, W, Cin, Cout, k = 24, 64, 64, 320, 320, 3
+    x = _rand((B, H, W, Cin), 1)
+    w = _rand((Cout, k * k * Cin), 2, scale=1.0 / math.sqrt(k * k * Cin))
+    y = ops.conv2d(x, w, None, k)
+    assert torch.isfinite(y.float()).all()
+    y2 = ops.conv2d((x.float() * 2).half(), w, None, k)
+    _assert_exactly_doubled(y2, y)
+    try:
+        ops.set_gemm_impl(1)
+        y_mma = ops.conv2d(x, w, None, k)
+    finally:
+        ops.set_gemm_impl(0)
+    assert _rel(y, y_mma) < 1e-3
+    # GEGLU feed-forward projection of the same batch (M = 98 304, K = 320, N = 2 560): value * gelu(gate) is
+    # homogeneous of degree 1 in the value half only -> scaling the value rows of the weight by 2 doubles the output
+    from gaussctrl_b200._lib import GCB_ACT_GEGLU
+    Cff = 2560
+    wff = _rand((Cff, Cin), 3, scale=1.0 / math.sqrt(Cin))
+    perm = ops.geglu_perm(Cff, x.device)                       # packed row r holds source row perm[r]
+    wp = wff[perm.long()].contiguous()
+    xt = x.reshape(1, 1, B * H * W, Cin)
+    g1 = ops.conv2d(xt, wp, None, 1, act=GCB_ACT_GEGLU)
+    w2 = wff.clone()
+    w2[: Cff // 2] = (wff[: Cff // 2].float() * 2).half()      # diffusers layout: rows [value | gate]
+    g2 = ops.conv2d(xt, w2[perm.long()].contiguous(), None, 1, act=GCB_ACT_GEGLU)
+    assert g1.shape[-1] == Cff // 2 and torch.isfinite(g1.float()).all()
+    _assert_exactly_doubled(g2, g1)
+
+
+# ------------------------------------------------------------------------------------------------ rasteriser
+def _scene_1m():
+    from bench import orbit_c2w, synthetic_scene
+    P = synthetic_scene(1_000_000, seed=0)
+    c2w = torch.eye(4)
+    c2w[:3] = orbit_c2w(3, 40)
+    return P, c2w, (539.05, 538.17, 258.74, 239.35), 512, 512
+
+
+def test_tile_binning_checksums_at_one_million_gaussians():
+    """Depth-ordered tile binning of the 1 M-Gaussian bench scene at 512x512: the intersection keys are sorted, every
+    Gaussian appears exactly once per tile it touches, and the tile bins partition [0, M) in tile order."""
+    from oracle import gsplat_ref as gr
+    from gaussctrl_b200 import gsplat_ops as go
+    P, c2w, (fx, fy, cx, cy), H, W = _scene_1m()
+    N = P["means"].shape[0]
+    vm = gr.viewmat_from_c2w(c2w)
+    pm = gr.projection_matrix(0.001, 1000, 2 * math.atan(W / (2 * fx)), 2 * math.atan(H / (2 * fy)))
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    scales = torch.exp(P["scales"]).cuda()
+    quats = (P["quats"] / P["quats"].norm(dim=-1, keepdim=True)).cuda()
+    with torch.no_grad():
+        xys, depths, radii, conics, nth, _ = go.project_gaussians(P["means"].cuda(), scales, 1, quats, vm[:3], pm @ vm, fx,
+                                                                  fy, cx, cy, H, W, tb)
+        gids, bins, keys, M = go.bin_and_sort(xys, depths, radii, nth, tb, want_keys=True)
+    torch.cuda.synchronize()
+    assert M == int(nth.sum().item()) and M > 1_000_000          # ~4.3 M intersections for this scene
+    k = keys.cpu().numpy()
+    assert (np.diff(k) >= 0).all()                                # sorted by (tile, depth bits)
+    assert torch.equal(torch.bincount(gids.long(), minlength=N), nth.long())   # multiplicity checksum
+    lens = (bins[:, 1] - bins[:, 0]).long()
+    assert int(lens.sum().item()) == M and int(lens.min().item()) >= 0
+    starts = torch.cumsum(lens, 0) - lens
+    nonempty = lens > 0
+    assert torch.equal(bins[:, 0].long()[nonempty], starts[nonempty])
+    tile_of_key = torch.repeat_interleave(torch.arange(bins.shape[0], device=bins.device), lens)
+    assert torch.equal(keys >> 32, tile_of_key)
+    # depth bits inside the key are the fp32 bits of the Gaussian's depth
+    low = (keys & 0xFFFFFFFF).to(torch.int32)
+    assert torch.equal(low, depths[gids.long()].view(torch.int32))
+
+
+def test_render_idempotent_and_in_range_at_one_million_gaussians():
+    """GaussCtrlModel eval render (fused project+SH front end, one binning, fused rgb+depth composite) of the bench
+    scene: bit-identical when repeated, colours and coverage in [0, 1], depth 1000 exactly where nothing was hit."""
+    from gaussctrl_b200.gc_model import render_gaussians
+    P, c2w, (fx, fy, cx, cy), H, W = _scene_1m()
+    Pc = {k: v.cuda() for k, v in P.items()}
+    bg = torch.zeros(3, device="cuda")
+    with torch.no_grad():
+        a = render_gaussians(Pc, c2w, fx, fy, cx, cy, H, W, 3, bg)
+        b = render_gaussians(Pc, c2w, fx, fy, cx, cy, H, W, 3, bg)
+    torch.cuda.synchronize()
+    for key in ("rgb", "depth", "accumulation"):
+        assert a[key].shape[:2] == (H, W) and torch.isfinite(a[key]).all()
+        assert torch.equal(a[key], b[key]), key
+    assert 0.0 <= a["rgb"].min().item() and a["rgb"].max().item() <= 1.0
+    assert 0.0 <= a["accumulation"].min().item() and a["accumulation"].max().item() <= 1.0 + 1e-6
+    hit = a["accumulation"][..., 0] > 0
+    assert hit.float().mean().item() > 0.3                         # the scene fills most of the view
+    assert (a["depth"][..., 0][~hit] == 1000.0).all() and (a["depth"][..., 0][hit] > 0).all()
