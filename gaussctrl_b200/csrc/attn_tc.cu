@@ -46,7 +46,10 @@ constexpr float RESCALE_THRESHOLD = 8.f;
 //             ex2: 487.5 -> 538.1 TFLOP/s (+10 %).
 //   SPLIT_LD (off): the second half of S still loading from TMEM while the row max of the first half is taken:
 //             484.7 TFLOP/s alone, 535.7 with SPLIT_ST - no gain, the TMEM-load latency is not what the max phase waits on.
+//   SPLIT_ST = 4 (not measured yet - the round's GPU budget ended): four pieces of 16 packed registers; the extra block
+//             boundaries come from re-waiting the already completed p_free phase (returns at once, but is a branch).
 constexpr bool ATTN_SPLIT_LD = GCB_ATTN_SPLIT_LD != 0, ATTN_SPLIT_ST = GCB_ATTN_SPLIT_ST != 0;
+constexpr bool ATTN_SPLIT_ST4 = GCB_ATTN_SPLIT_ST == 4;
 constexpr int ATTN_LAG = GCB_ATTN_LAG;  // 0 = off, 1 = slot 0 signals after its row max, 2 = after half of its exponentials
 
 template <int D_>
@@ -177,6 +180,17 @@ __device__ __forceinline__ void tmem_st32_from(uint32_t taddr, const uint32_t (&
           "r"(r[OFF + 18]), "r"(r[OFF + 19]), "r"(r[OFF + 20]), "r"(r[OFF + 21]), "r"(r[OFF + 22]), "r"(r[OFF + 23]),
           "r"(r[OFF + 24]), "r"(r[OFF + 25]), "r"(r[OFF + 26]), "r"(r[OFF + 27]), "r"(r[OFF + 28]), "r"(r[OFF + 29]),
           "r"(r[OFF + 30]), "r"(r[OFF + 31])
+        : "memory");
+}
+
+template <int OFF, int NR>
+__device__ __forceinline__ void tmem_st16_from(uint32_t taddr, const uint32_t (&r)[NR]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[OFF + 0]), "r"(r[OFF + 1]), "r"(r[OFF + 2]), "r"(r[OFF + 3]), "r"(r[OFF + 4]), "r"(r[OFF + 5]),
+          "r"(r[OFF + 6]), "r"(r[OFF + 7]), "r"(r[OFF + 8]), "r"(r[OFF + 9]), "r"(r[OFF + 10]), "r"(r[OFF + 11]),
+          "r"(r[OFF + 12]), "r"(r[OFF + 13]), "r"(r[OFF + 14]), "r"(r[OFF + 15])
         : "memory");
 }
 
@@ -477,7 +491,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 };
                 using std::integral_constant;
-                if (ATTN_SPLIT_ST && BN == 128) {
+                if (ATTN_SPLIT_ST4 && BN == 128) {
+                    const uint32_t pf = smem_u32(&sm.p_free[t]), pf_par = ((uint32_t)(i - 1)) & 1u;
+                    exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 8>{});            // keys 0..31
+                    mbar_wait(pf, pf_par);  // the real wait (i == 0: parity 1 of a fresh barrier passes at once)
+                    tc_fence_after();
+                    tmem_st16_from<0>(p_t, sr);
+                    exp_block(integral_constant<int, BN / 8>{}, integral_constant<int, BN / 4>{});       // keys 32..63
+                    mbar_wait(pf, pf_par);  // completed phase: only a basic-block boundary
+                    tmem_st16_from<(BN == 128 ? 16 : 0)>(p_t + 16, sr);
+                    exp_block(integral_constant<int, BN / 4>{}, integral_constant<int, 3 * BN / 8>{});   // keys 64..95
+                    mbar_wait(pf, pf_par);
+                    tmem_st16_from<(BN == 128 ? 32 : 0)>(p_t + 32, sr);
+                    exp_block(integral_constant<int, 3 * BN / 8>{}, integral_constant<int, BN / 2>{});   // keys 96..127
+                    l += (l0 + l1) + (l2 + l3);
+                    tmem_st16_from<(BN == 128 ? 48 : 0)>(p_t + 48, sr);
+                } else if (ATTN_SPLIT_ST && BN == 128) {
                     exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 4>{});   // keys 0..63
                     if (!waited) {
                         mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
