@@ -41,3 +41,13 @@ def test_b200_parameter_table_matches_transformers_names():
         bad = dict(sd)
         bad.pop("text_model.final_layer_norm.bias")
         ct.check_clip_state_dict(bad)
+
+
+def test_prompt_encoder_factory_without_checkpoint(tmp_path):
+    """No tokenizer/ + text_encoder/ under the checkpoint folder -> None (the pipeline then keeps its synthetic
+    embeddings); a hub name is never resolved (no network)."""
+    from gaussctrl_b200.clip_text import make_prompt_encoder
+    assert make_prompt_encoder(str(tmp_path), "cuda") is None
+    (tmp_path / "tokenizer").mkdir()
+    assert make_prompt_encoder(str(tmp_path), "cuda") is None      # text_encoder/model.safetensors still missing
+    assert make_prompt_encoder("CompVis/stable-diffusion-v1-4", "cuda") is None
