@@ -164,6 +164,25 @@ def attention(q: torch.Tensor, q_off: int, ld_q: int, kv: torch.Tensor, k_off: i
     return out
 
 
+def attention_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, d: int, src_index: torch.Tensor,
+                  weights: Sequence[float], scale: Optional[float] = None) -> torch.Tensor:
+    """Multi-source attention on separate contiguous projections: q [B,Nq,h*d], k/v [Bk,Nk,h*d] fp16 (the layout a
+    diffusers `Attention` module's to_q/to_k/to_v produce; utils.CrossViewAttnProcessor).  src_index [B,n_src] rows of k/v."""
+    _f16(q), _f16(k), _f16(v)
+    B, Nq, C = q.shape
+    assert C == heads * d and k.shape == v.shape and k.shape[-1] == C, (q.shape, k.shape, v.shape, heads, d)
+    Nk = k.shape[1]
+    n_src = len(weights)
+    assert src_index.dtype == torch.int32 and src_index.numel() == B * n_src and src_index.is_cuda
+    out = torch.empty((B, Nq, C), dtype=torch.float16, device=q.device)
+    w = (ctypes.c_float * n_src)(*[float(x) for x in weights])
+    sc = d ** -0.5 if scale is None else float(scale)
+    check(lib.gcb_attn_multi_fwd(_p(q), C, _p(k), _p(v), C, None, None, 0, _p(out), C, B, Nq, Nk, heads, d, d, n_src,
+                                 _p(src_index), w, sc, _ATTN_IMPL[0], _stream()))
+    LAUNCHES[0] += 1
+    return out
+
+
 def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:
     y = torch.empty_like(_f16(x))
     cols = x.shape[-1]

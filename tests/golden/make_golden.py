@@ -76,6 +76,28 @@ def crossview_cases():
     print("crossview_reference.npz:", len(cases), "cases")
 
 
+def native_crossview_cases():
+    """Reference utils.py at the shapes the sm_100a kernels take natively (8 heads; N=256 d=40/80 -> tcgen05, d=160 and
+    the 77 text keys -> mma.sync; F=12 = R=8 + c=4).  Only the OUTPUT (every 16th token + token mean) and an input
+    fingerprint are stored; inputs are regenerated from the seed by tests/golden/native_cases.py."""
+    from native_cases import NATIVE_CASES, fingerprint, native_case_inputs, subsample
+    ref_utils = load_reference_utils()
+    out = {}
+    for name in NATIVE_CASES:
+        sd, hs, ehs, (heads, dh, n, f, coeff, cross, ntext) = native_case_inputs(name)
+        attn = AttentionStub(heads * dh, heads, dh, cross_attention_dim=cross)
+        attn.load_state_dict(sd)
+        proc = ref_utils.CrossViewAttnProcessor(self_attn_coeff=coeff, unet_chunk_size=2)
+        with torch.no_grad():
+            y = proc(attn, hs, encoder_hidden_states=ehs)
+        sub, mean = subsample(y)
+        out[f"{name}.out_sub"] = sub
+        out[f"{name}.out_mean"] = mean
+        out[f"{name}.fingerprint"] = np.frombuffer(fingerprint(sd, hs, ehs).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "crossview_native_reference.npz"), **out)
+    print("crossview_native_reference.npz:", len(NATIVE_CASES), "cases")
+
+
 def extract_methods(path, class_name, names):
     src = open(path).read()
     tree = ast.parse(src)
@@ -122,5 +144,7 @@ def glue_cases():
 
 if __name__ == "__main__":
     assert os.path.isdir(REF), "run this where /root/reference is mounted"
+    sys.path.insert(0, HERE)
     crossview_cases()
+    native_crossview_cases()
     glue_cases()
