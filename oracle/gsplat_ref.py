@@ -264,6 +264,42 @@ def bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds):
     return keys_s, gids_s, bins
 
 
+def bin_and_sort_vectorized(xys, depths, radii, num_tiles_hit, tile_bounds):
+    """Same result as `bin_and_sort` without the per-Gaussian Python loop (numpy repeat/arange instead), for the
+    full-size parity tests (1 M Gaussians, ~4 M intersections).  tests/test_raster_cpu.py checks it equals the loop."""
+    xys_n = xys.detach().cpu().numpy().astype(np.float32)
+    dep_n = depths.detach().cpu().numpy().astype(np.float32)
+    rad_n = radii.detach().cpu().numpy().astype(np.int32)
+    nth = num_tiles_hit.detach().cpu().numpy().astype(np.int64)
+    tbx, tby = int(tile_bounds[0]), int(tile_bounds[1])
+    blk = np.float32(BLOCK)
+    tcx, tcy, tr = xys_n[:, 0] / blk, xys_n[:, 1] / blk, rad_n.astype(np.float32) / blk
+    trunc = lambda a: np.trunc(a).astype(np.int64)  # noqa: E731  (Python int() of a float truncates toward zero)
+    x0 = np.clip(trunc(tcx - tr), 0, tbx)
+    x1 = np.clip(trunc((tcx + tr) + np.float32(1.0)), 0, tbx)
+    y0 = np.clip(trunc(tcy - tr), 0, tby)
+    y1 = np.clip(trunc((tcy + tr) + np.float32(1.0)), 0, tby)
+    wdt = x1 - x0
+    cnt = np.where(rad_n > 0, wdt * (y1 - y0), 0)
+    assert np.array_equal(cnt, nth), "num_tiles_hit does not match the tile bounding boxes"
+    M = int(cnt.sum())
+    g_of = np.repeat(np.arange(len(cnt), dtype=np.int64), cnt)
+    local = np.arange(M, dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    wg = np.maximum(wdt[g_of], 1)
+    tile = (y0[g_of] + local // wg) * tbx + (x0[g_of] + local % wg)
+    depth_bits = dep_n.view(np.int32).astype(np.int64) & 0xFFFFFFFF
+    keys = (tile << 32) | depth_bits[g_of]
+    order = np.argsort(keys, kind="stable")
+    keys_s, gids_s = keys[order], g_of[order].astype(np.int32)
+    ntiles = tbx * tby
+    bins = np.zeros((ntiles, 2), dtype=np.int32)
+    if M:
+        tile_of = keys_s >> 32
+        bins[:, 0] = np.searchsorted(tile_of, np.arange(ntiles), side="left")
+        bins[:, 1] = np.searchsorted(tile_of, np.arange(ntiles), side="right")
+    return keys_s, gids_s, bins
+
+
 def rasterize_sorted(xys, conics, colors, opacities, gids_sorted, tile_bins, img_height, img_width,
                      background: Optional[torch.Tensor]):
     """rasterize_forward for C channels, differentiable (autograd = backward oracle).
@@ -274,23 +310,26 @@ def rasterize_sorted(xys, conics, colors, opacities, gids_sorted, tile_bins, img
     tbx = (W + BLOCK - 1) // BLOCK
     tby = (H + BLOCK - 1) // BLOCK
     opac = opacities.reshape(-1)
+    dev = colors.device  # CPU in the small-size tests; the full-size GPU parity tests run this same code in fp32 on CUDA
     if background is None:
-        background = torch.ones(C, dtype=colors.dtype)
+        background = torch.ones(C, dtype=colors.dtype, device=dev)
+    background = background.to(dev)
     img_rows = [[None] * tbx for _ in range(tby)]
     alpha_rows = [[None] * tbx for _ in range(tby)]
     fidx = np.zeros((H, W), dtype=np.int32)
-    gids_t = torch.as_tensor(np.asarray(gids_sorted), dtype=torch.long)
+    gids_t = torch.as_tensor(np.asarray(gids_sorted), dtype=torch.long).to(dev)
+    tile_bins = np.asarray(tile_bins.cpu() if isinstance(tile_bins, torch.Tensor) else tile_bins)
     for ti in range(tby):
         for tj in range(tbx):
             h0, w0 = ti * BLOCK, tj * BLOCK
             hh, ww = min(BLOCK, H - h0), min(BLOCK, W - w0)
             start, end = int(tile_bins[ti * tbx + tj][0]), int(tile_bins[ti * tbx + tj][1])
-            py = torch.arange(h0, h0 + hh, dtype=torch.float32)[:, None].expand(hh, ww).reshape(-1)
-            px = torch.arange(w0, w0 + ww, dtype=torch.float32)[None, :].expand(hh, ww).reshape(-1)
+            py = torch.arange(h0, h0 + hh, dtype=torch.float32, device=dev)[:, None].expand(hh, ww).reshape(-1)
+            px = torch.arange(w0, w0 + ww, dtype=torch.float32, device=dev)[None, :].expand(hh, ww).reshape(-1)
             P = hh * ww
             if end <= start:
                 img_rows[ti][tj] = background[None, :].expand(P, C).reshape(hh, ww, C)
-                alpha_rows[ti][tj] = torch.zeros(hh, ww)
+                alpha_rows[ti][tj] = torch.zeros(hh, ww, device=dev)
                 continue
             ids = gids_t[start:end]
             xy, con, col, op = xys[ids], conics[ids], colors[ids], opac[ids]
@@ -302,14 +341,14 @@ def rasterize_sorted(xys, conics, colors, opacities, gids_sorted, tile_bins, img
             a_eff = torch.where(keep, alpha, torch.zeros_like(alpha))
             one_m = 1.0 - a_eff
             T_incl = torch.cumprod(one_m, dim=1)                       # T after each Gaussian
-            T_excl = torch.cat([torch.ones(P, 1), T_incl[:, :-1]], dim=1)
+            T_excl = torch.cat([torch.ones(P, 1, device=dev), T_incl[:, :-1]], dim=1)
             with torch.no_grad():
                 stop = keep & (T_incl <= 1e-4)                          # first Gaussian that would end the pixel
                 stopped = torch.cumsum(stop.to(torch.int32), dim=1) > 0  # at and after that Gaussian: no contribution
                 active = keep & ~stopped
                 any_stop = stopped[:, -1]
                 first_stop = torch.argmax(stopped.to(torch.int32), dim=1)
-                pos = torch.arange(end - start)[None, :].expand(P, -1)
+                pos = torch.arange(end - start, device=dev)[None, :].expand(P, -1)
                 last = torch.where(active, pos, torch.full_like(pos, -1)).max(dim=1).values
             vis = torch.where(active, a_eff * T_excl, torch.zeros_like(a_eff))
             out = vis @ col
@@ -319,7 +358,7 @@ def rasterize_sorted(xys, conics, colors, opacities, gids_sorted, tile_bins, img
             img_rows[ti][tj] = out.reshape(hh, ww, C)
             alpha_rows[ti][tj] = (1.0 - T_final).reshape(hh, ww)
             fidx[h0:h0 + hh, w0:w0 + ww] = (torch.where(last >= 0, last + start, torch.zeros_like(last))
-                                            .reshape(hh, ww).numpy())
+                                            .reshape(hh, ww).cpu().numpy())
     img = torch.cat([torch.cat(r, dim=1) for r in img_rows], dim=0)
     alpha = torch.cat([torch.cat(r, dim=1) for r in alpha_rows], dim=0)
     return img, alpha, fidx

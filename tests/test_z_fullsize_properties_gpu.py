@@ -4,7 +4,6 @@ comparison - convexity and linearity of attention in V, exact power-of-two homog
 kernel for the convolutions, sortedness / multiplicity checksums of the tile binning, idempotence and range of the
 render.  (Element-wise parity against the oracle at small sizes: test_kernels_gpu.py, test_raster_gpu.py.)"""
 import math
-import warnings
 
 import numpy as np
 import pytest
@@ -30,15 +29,14 @@ def _rel(a, b):
 
 
 def _assert_same(a, b, what, rel_tol=1e-3):
-    """The property is exact on paper (bit-identical results).  These full-size checks were written after the round's GPU
-    budget was spent, so a violation of exactness that still meets the fp16 tolerance is reported as a warning instead
-    of a failure; a violation of the tolerance fails."""
+    """The property is exact (bit-identical results): the refs-once schedule and the multi-GPU parity argument depend on
+    batch-invariant, deterministic kernels, so any differing element fails (first executed green at the end of round 1)."""
     if torch.equal(a, b):
         return
     rel = _rel(a, b)
     frac = (a != b).float().mean().item()
-    assert rel < rel_tol, (what, rel, frac)
-    warnings.warn(f"{what}: expected bit-identical results, got rel {rel:.2e} with {frac:.2%} of the elements different")
+    raise AssertionError(f"{what}: expected bit-identical results, got rel {rel:.2e} with {frac:.2%} of the elements "
+                         f"different")
 
 
 def _assert_exactly_doubled(y2, y, what):
@@ -48,7 +46,7 @@ def _assert_exactly_doubled(y2, y, what):
     normal = y.abs() >= 2.0 ** -13
     _assert_same(y2[normal], y[normal] * 2, what)
     if (~normal).any():
-        assert (y2[~normal] - y[~normal] * 2).abs().max().item() <= 2.0 ** -12
+        assert (y2[~normal] - y[~normal] * 2).abs().max().item() <= 2.0 ** -23
 
 
 # ------------------------------------------------------------------------------------------------ attention
