@@ -172,7 +172,7 @@ class EditEngine:
     @torch.no_grad()
     def edit_reference_schedule(self, latents: torch.Tensor, disparity: torch.Tensor, pos_embed: torch.Tensor,
                                 neg_embed: torch.Tensor, S: int, guidance: float, num_ref: int,
-                                ref_frames: Sequence[int] = (0, 1, 2, 3)) -> torch.Tensor:
+                                ref_frames: Sequence[int] = (0, 1, 2, 3), stop_after: Optional[int] = None) -> torch.Tensor:
         """One `pipe(...)` call of edit_images exactly as the reference batches it (gc_pipeline.py:206-219):
         latents [F,4,h,w] = [refs | chunk], CFG rows [uncond x F | cond x F].  Returns the final latents of the
         chunk rows [F-num_ref,4,h,w] (decode is the VAE's job)."""
@@ -186,7 +186,7 @@ class EditEngine:
         st = self._steps[key]
         st.x.copy_(self._latents_in(latents))
         st.set_cond(self._cond_emb(disparity))
-        for t in self.tables.timesteps(S):
+        for t in list(self.tables.timesteps(S))[:stop_after]:  # stop_after: parity tests truncate long schedules
             st.run(t, self.tables.step_coefs(t, S))
         return ops.nhwc_to_nchw(st.x[num_ref:].contiguous())
 
@@ -194,7 +194,7 @@ class EditEngine:
     def edit_refs_once(self, latents: torch.Tensor, disparity: torch.Tensor, ref_indices: Sequence[int],
                        pos_embed: torch.Tensor, neg_embed: torch.Tensor, S: int, guidance: float, view_batch: int = 4,
                        ref_frames: Sequence[int] = (0, 1, 2, 3), view_ids: Optional[Sequence[int]] = None,
-                       dist_ctx: Optional[dict] = None) -> torch.Tensor:
+                       dist_ctx: Optional[dict] = None, stop_after: Optional[int] = None) -> torch.Tensor:
         """Edit all V views: latents [V,4,h,w] (z_T of every view), disparity [V,3,H,W], ref_indices = the R reference
         view ids.  Per DDIM step: (1) the R references are denoised once, recording every self-attention layer's
         K/V; (2) the remaining views are denoised in batches of `view_batch`, reading that K/V.
@@ -242,7 +242,7 @@ class EditEngine:
             padded = b + [b[-1]] * (bsz - len(b))
             x_views.append(x_all[padded].clone())
             conds.append(torch.stack([cond_map[v] for v in padded]))
-        for t in self.tables.timesteps(S):
+        for t in list(self.tables.timesteps(S))[:stop_after]:
             coefs = self.tables.step_coefs(t, S)
             ref_step.run(t, coefs)
             if batches and view_step is None:

@@ -62,7 +62,7 @@ def invert_view(unet, cnet, tables: sd15.DDIMTables, z0, disparity, prompt_embed
 @torch.no_grad()
 def edit_chunk(unet, cnet, vae, tables: sd15.DDIMTables, latents, disparity, pos_embed, neg_embed, S: int,
                guidance_scale: float, num_ref: int, ref_frames: Sequence[int] = (0, 1, 2, 3),
-               decode: bool = True, return_latents: bool = False):
+               decode: bool = True, return_latents: bool = False, stop_after: Optional[int] = None):
     """One `pipe(...)` call of edit_images (gc_pipeline.py:209-219) on F = R + c frames.
 
     latents [F,4,h,w], disparity [F,3,H,W]; pos/neg_embed [1,77,D].  CFG batch = cat([uncond, cond]) (2F rows),
@@ -75,7 +75,7 @@ def edit_chunk(unet, cnet, vae, tables: sd15.DDIMTables, latents, disparity, pos
     ehs = torch.cat([neg_embed.expand(F_, -1, -1), pos_embed.expand(F_, -1, -1)], dim=0)
     cond = torch.cat([disparity] * 2, dim=0)
     x = latents
-    for t in tables.timesteps(S):
+    for t in list(tables.timesteps(S))[:stop_after]:  # stop_after: test-only truncation of a long schedule (cfg5: S=50)
         xin = torch.cat([x] * 2, dim=0)
         down, mid = cnet(xin, int(t), ehs, cond, 1.0)
         eps = unet(xin, int(t), ehs, down, mid)

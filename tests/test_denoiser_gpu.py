@@ -148,3 +148,52 @@ def test_inversion_matches_oracle(models):
                                  pos.cuda(), S)
         rel = _rel(got[v:v + 1], want)
         assert rel < 2e-2, rel
+
+
+def test_edit_loop_cfg4_eight_references(models):
+    """BASELINE cfg4 layout: ref_view_num=8 -> the chunk batch is [8 refs | c views] and the reference's hard-coded
+    frames 0..3 (utils.py:95-98) make only the FIRST FOUR references K/V sources; refs 4..7 are ordinary batch rows.
+    Both schedules against the oracle's literal loop."""
+    from oracle import pipeline as opipe, sd15
+    from gaussctrl_b200.engine import EditEngine
+    unet, cnet, den = models
+    R, c, S, g = 8, 2, 3, 5.0
+    lat, disp, pos, neg = _inputs(R + c, seed=5)
+    want = opipe.edit_chunk(unet, cnet, None, sd15.DDIMTables(), lat.cuda(), disp.cuda(), pos.cuda(), neg.cuda(), S, g, R,
+                            decode=False)
+    eng = EditEngine(den, use_graphs=True)
+    got = eng.edit_reference_schedule(lat, disp, pos, neg, S, g, R, ref_frames=(0, 1, 2, 3))
+    assert _rel(got, want) < 2e-2
+    got2 = eng.edit_refs_once(lat, disp, list(range(R)), pos, neg, S, g, view_batch=2, ref_frames=(0, 1, 2, 3))
+    assert _rel(got2[R:], want) < 2e-2
+    assert _rel(got2[R:], got) < 1e-3   # the two schedules agree with each other far inside the oracle band
+
+
+def test_edit_loop_cfg5_guidance_7p5_first_10_of_50_steps(models):
+    """BASELINE cfg5: guidance 7.5, 50-step schedule (first 10 steps run here), chunk_size 4."""
+    from oracle import pipeline as opipe, sd15
+    from gaussctrl_b200.engine import EditEngine
+    unet, cnet, den = models
+    R, c, S, g, run = 4, 4, 50, 7.5, 10
+    lat, disp, pos, neg = _inputs(R + c, seed=6)
+    want = opipe.edit_chunk(unet, cnet, None, sd15.DDIMTables(), lat.cuda(), disp.cuda(), pos.cuda(), neg.cuda(), S, g, R,
+                            decode=False, stop_after=run)
+    eng = EditEngine(den, use_graphs=True)
+    got = eng.edit_reference_schedule(lat, disp, pos, neg, S, g, R, stop_after=run)
+    rel = _rel(got, want)
+    assert rel < 3e-2, rel   # 10 fp16 steps with a 7.5x guidance amplification of the eps difference
+
+
+def test_edit_loop_20_step_drift_bound(models):
+    """The metric's full 20-step schedule on one cfg2 chunk (R=4, c=3): fp16 product vs fp32 oracle drift."""
+    from oracle import pipeline as opipe, sd15
+    from gaussctrl_b200.engine import EditEngine
+    unet, cnet, den = models
+    R, c, S, g = 4, 3, 20, 5.0
+    lat, disp, pos, neg = _inputs(R + c, seed=7)
+    want = opipe.edit_chunk(unet, cnet, None, sd15.DDIMTables(), lat.cuda(), disp.cuda(), pos.cuda(), neg.cuda(), S, g, R,
+                            decode=False)
+    eng = EditEngine(den, use_graphs=True)
+    got = eng.edit_refs_once(lat, disp, list(range(R)), pos, neg, S, g, view_batch=3)[R:]
+    rel = _rel(got, want)
+    assert torch.isfinite(got.float()).all() and rel < 5e-2, rel
