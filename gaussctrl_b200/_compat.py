@@ -9,13 +9,25 @@ from typing import Any, Optional, Type
 
 import torch
 
-try:  # pragma: no cover - exercised only where nerfstudio exists
+try:  # exercised by tests/test_plugin_seam_cpu.py against a fake `nerfstudio` tree that enforces the same contracts
     from nerfstudio.cameras.cameras import Cameras  # type: ignore
+    from nerfstudio.data.datamanagers.full_images_datamanager import (  # type: ignore
+        FullImageDatamanager, FullImageDatamanagerConfig)
+    from nerfstudio.model_components import renderers  # type: ignore
     from nerfstudio.models.splatfacto import SplatfactoModel, SplatfactoModelConfig  # type: ignore
     from nerfstudio.pipelines.base_pipeline import VanillaPipeline, VanillaPipelineConfig  # type: ignore
     HAVE_NERFSTUDIO = True
-except Exception:  # ModuleNotFoundError here
+except ModuleNotFoundError:
     HAVE_NERFSTUDIO = False
+    import types as _types
+
+    renderers = _types.SimpleNamespace(BACKGROUND_COLOR_OVERRIDE=None)  # nerfstudio.model_components.renderers
+
+    class _InstantiateConfig:
+        """nerfstudio.configs.base_config.InstantiateConfig: `setup(**kwargs)` builds `_target(self, **kwargs)`."""
+
+        def setup(self, **kwargs):
+            return self._target(self, **kwargs)
 
     class Cameras:  # the attributes GaussCtrlModel.get_outputs reads (gc_model.py:65-113)
         def __init__(self, camera_to_worlds, fx, fy, cx, cy, width, height):
@@ -51,12 +63,15 @@ except Exception:  # ModuleNotFoundError here
             return None
 
     @dataclass
-    class SplatfactoModelConfig:
+    class SplatfactoModelConfig(_InstantiateConfig):
         _target: Type = field(default_factory=lambda: SplatfactoModel)
         sh_degree: int = 3
         sh_degree_interval: int = 1000
         background_color: str = "random"
         ssim_lambda: float = 0.2
+        use_scale_regularization: bool = False
+        max_gauss_ratio: float = 10.0
+        stop_split_at: int = 15000
 
     class SplatfactoModel(torch.nn.Module):
         """Owns the Gaussian parameters under the nerfstudio names (gc_model.py:124-136 reads them)."""
@@ -65,7 +80,7 @@ except Exception:  # ModuleNotFoundError here
             super().__init__()
             self.config = config if config is not None else SplatfactoModelConfig()
             P = torch.nn.Parameter
-            n = num_points
+            n = num_points if seed_points is None else int(seed_points[0].shape[0])
             self.means = P(torch.zeros(n, 3))
             self.scales = P(torch.zeros(n, 3))
             self.quats = P(torch.zeros(n, 4))
@@ -102,19 +117,55 @@ except Exception:  # ModuleNotFoundError here
             return {"psnr": 10.0 * torch.log10(1.0 / mse), "gaussian_count": self.means.shape[0]}
 
     @dataclass
-    class VanillaPipelineConfig:
+    class FullImageDatamanagerConfig(_InstantiateConfig):
+        """The fields of nerfstudio 1.0.0's FullImageDatamanagerConfig that the hot path or its callers read."""
+        _target: Type = field(default_factory=lambda: FullImageDatamanager)
+        dataparser: Any = None
+        camera_res_scale_factor: float = 1.0
+        eval_num_images_to_sample_from: int = -1
+        eval_num_times_to_repeat_images: int = -1
+        eval_image_indices: Optional[tuple] = (0,)
+        cache_images: str = "cpu"
+        cache_images_type: str = "float32"
+
+    class FullImageDatamanager(torch.nn.Module):
+        """Stand-in: holds `train_dataset`/`cached_train` when a dataparser is configured; nothing else."""
+
+        def __init__(self, config=None, device="cpu", test_mode="val", world_size=1, local_rank=0, **_):
+            super().__init__()
+            self.config, self.device, self.test_mode = config, device, test_mode
+            self.world_size, self.local_rank = world_size, local_rank
+            self.train_dataset = None
+            self.eval_dataset = None
+            self.cached_train: list = []
+
+    @dataclass
+    class VanillaPipelineConfig(_InstantiateConfig):
         _target: Type = field(default_factory=lambda: VanillaPipeline)
         datamanager: Any = None
         model: Any = None
 
     class VanillaPipeline(torch.nn.Module):
+        """Same constructor contract as nerfstudio 1.0.0's VanillaPipeline: the datamanager and the model are BUILT
+        from their configs (`config.datamanager.setup(...)`, `config.model.setup(...)`)."""
+
         def __init__(self, config=None, device="cpu", test_mode="val", world_size=1, local_rank=0, grad_scaler=None):
             super().__init__()
             self.config = config
             self.test_mode = test_mode
+            self.datamanager = config.datamanager.setup(device=device, test_mode=test_mode, world_size=world_size,
+                                                        local_rank=local_rank)
+            seed_pts = None
+            dpo = getattr(self.datamanager, "train_dataparser_outputs", None)
+            if dpo is not None and "points3D_xyz" in dpo.metadata:
+                seed_pts = (dpo.metadata["points3D_xyz"], dpo.metadata["points3D_rgb"])
+            assert self.datamanager.train_dataset is not None, "Missing input dataset"
+            self._model = config.model.setup(scene_box=self.datamanager.train_dataset.scene_box,
+                                             num_train_data=len(self.datamanager.train_dataset),
+                                             metadata=self.datamanager.train_dataset.metadata, device=device,
+                                             grad_scaler=grad_scaler, seed_points=seed_pts)
+            self._model.to(device)
             self.world_size = world_size
-            self.datamanager = None
-            self._model = None
 
         @property
         def model(self):

@@ -12,7 +12,7 @@ from typing import Dict, List, Optional, Type, Union
 import torch
 
 from . import gsplat_ops
-from ._compat import Cameras, SplatfactoModel, SplatfactoModelConfig
+from ._compat import Cameras, SplatfactoModel, SplatfactoModelConfig, renderers
 
 
 def projection_matrix(znear: float, zfar: float, fovx: float, fovy: float, device="cpu") -> torch.Tensor:
@@ -114,6 +114,8 @@ class GaussCtrlModel(SplatfactoModel):
                 background = torch.zeros(3, device=self.device)
             else:
                 background = self.background_color.to(self.device)
+        elif renderers.BACKGROUND_COLOR_OVERRIDE is not None:      # gc_model.py:84-85 (ns-render's background override)
+            background = renderers.BACKGROUND_COLOR_OVERRIDE.to(self.device)
         else:
             background = self.background_color.to(self.device)
         params = {k: getattr(self, k) for k in ("means", "scales", "quats", "features_dc", "features_rest", "opacities")}
@@ -122,26 +124,53 @@ class GaussCtrlModel(SplatfactoModel):
             if crop_ids.sum() == 0:
                 return {"rgb": background.repeat(int(camera.height.item()), int(camera.width.item()), 1)}
             params = {k: v[crop_ids] for k, v in params.items()}
-        W, H = int(camera.width.item()), int(camera.height.item())
-        self.last_size = (H, W)
+        # splatfacto's resolution schedule (gc_model.py:96-97, :170): intrinsics and size are read at the downscaled
+        # resolution and the camera is restored afterwards
+        camera_downscale = self._get_downscale_factor()
+        camera.rescale_output_resolution(1 / camera_downscale)
+        try:
+            W, H = int(camera.width.item()), int(camera.height.item())
+            self.last_size = (H, W)
+            intr = (camera.fx.item(), camera.fy.item(), camera.cx.item(), camera.cy.item())
+        finally:
+            camera.rescale_output_resolution(camera_downscale)
         sh_degree = getattr(self.config, "sh_degree", 3)
         n = min(self.step // getattr(self.config, "sh_degree_interval", 1000), sh_degree) if sh_degree > 0 else -1
         state: dict = {}
-        out = render_gaussians(params, camera.camera_to_worlds[0], camera.fx.item(), camera.fy.item(), camera.cx.item(),
-                               camera.cy.item(), H, W, n, background, training=self.training, state=state)
+        out = render_gaussians(params, camera.camera_to_worlds[0], *intr, H, W, n, background, training=self.training,
+                               state=state)
         self.xys, self.radii = state.get("xys"), state.get("radii")
+        # gc_model.py:159-160: splatfacto's after_train densification callback reads `self.xys.grad`
+        if self.training and self.xys is not None and self.xys.requires_grad:
+            self.xys.retain_grad()
         return out
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
         """nerfstudio 1.0.0 SplatfactoModel.get_loss_dict (what gc_pipeline.py:283-285 calls; the reference's
         GaussCtrlModel inherits it): main_loss = (1-l)*L1 + l*(1-SSIM) with the loss AND its gradient w.r.t. the
-        render from one fused C-ABI call (finetune.l1_ssim_loss).  Scale regularisation is off in the reference's
-        config (use_scale_regularization default False) -> 0."""
+        render from one fused C-ABI call (finetune.l1_ssim_loss); `batch["mask"]` blacks out both images first;
+        scale regularisation (off by default: use_scale_regularization False) every 10th step as splatfacto does."""
         from .finetune import l1_ssim_loss
         gt = self.get_gt_img(batch["image"]) if hasattr(self, "get_gt_img") else batch["image"].to(self.device)
-        main_loss, parts = l1_ssim_loss(outputs["rgb"], gt, float(getattr(self.config, "ssim_lambda", 0.2)))
+        pred = outputs["rgb"]
+        if "mask" in batch:
+            # splatfacto: masked-out pixels are black in both images
+            mask = batch["mask"]
+            if hasattr(self, "_downscale_if_required"):
+                mask = self._downscale_if_required(mask)
+            mask = mask.to(self.device).to(pred.dtype)
+            assert mask.shape[:2] == gt.shape[:2] == pred.shape[:2]
+            gt, pred = gt * mask, pred * mask
+        main_loss, parts = l1_ssim_loss(pred, gt, float(getattr(self.config, "ssim_lambda", 0.2)))
         self.last_loss_parts = parts  # device float[3]: (main_loss, L1, ssim) - no host sync here
-        return {"main_loss": main_loss, "scale_reg": torch.zeros((), device=main_loss.device)}
+        if getattr(self.config, "use_scale_regularization", False) and self.step % 10 == 0:
+            ratio = float(getattr(self.config, "max_gauss_ratio", 10.0))
+            scale_exp = torch.exp(self.scales)
+            scale_reg = torch.clamp(scale_exp.amax(dim=-1) / scale_exp.amin(dim=-1), min=ratio) - ratio
+            scale_reg = 0.1 * scale_reg.mean()
+        else:
+            scale_reg = torch.zeros((), device=main_loss.device)
+        return {"main_loss": main_loss, "scale_reg": scale_reg}
 
     @torch.no_grad()
     def get_outputs_for_camera(self, camera: Cameras, obb_box=None) -> Dict[str, torch.Tensor]:

@@ -3,7 +3,10 @@
 Same config fields and defaults, same constructor signature, same methods (`render_reverse`, `edit_images`,
 `image2latent`, `depth2disparity`, `depth2disparity_torch`, `update_datasets`) and the same `train_data[i]` dict schema
 (`image`, `image_idx`, `unedited_image`, `depth_image`, `z_0_image`, `mask_image`; dtypes/shapes of
-gc_pipeline.py:268-274 and :234), so the reference's trainer (`gc_trainer.py:75-78`) drives it unchanged.
+gc_pipeline.py:268-274 and :234): the calls the reference's trainer makes (`gc_trainer.py:75-78`, `:272`) are all here.
+The constructor builds datamanager and model from `config.datamanager` / `config.model` exactly like nerfstudio's
+VanillaPipeline (that contract is exercised against a fake `nerfstudio` tree in tests/test_plugin_seam_cpu.py; the
+real package is not installable in this image).
 What changed is below the seam: rasterisation, VAE, ControlNet+UNet, cross-view attention and the DDIM updates are
 the sm_100a kernels of this package, views are batched, and the reference views are denoised once per step instead
 of once per chunk (engine.EditEngine.edit_refs_once)."""
@@ -20,6 +23,7 @@ import torch
 
 from . import ops
 from ._compat import HAVE_NERFSTUDIO, VanillaPipeline, VanillaPipelineConfig
+from .gc_datamanager import GaussCtrlDataManagerConfig
 from .diffusion import SD15Denoiser
 from .engine import EditEngine
 from .sd15_spec import DDIMTables, synthetic_weights
@@ -48,6 +52,10 @@ def crossview_ref_frames(ref_view_num: int) -> tuple:
     return tuple(range(min(int(ref_view_num), 4)))
 
 
+def _pinned(t: torch.Tensor) -> torch.Tensor:
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
 def synthetic_prompt_embeds(prompts: Sequence[str], seq: int = 77, dim: int = 768) -> torch.Tensor:
     """Stand-in for the CLIP text encoder when no checkpoint is on disk: a deterministic N(0,1) embedding per prompt
     string.  (CLIP itself is outside the hot path: it runs once per `pipe()` call in the reference.)"""
@@ -62,7 +70,7 @@ def synthetic_prompt_embeds(prompts: Sequence[str], seq: int = 77, dim: int = 76
 class GaussCtrlPipelineConfig(VanillaPipelineConfig):
     """Field names, types and defaults of gaussctrl/gc_pipeline.py:48-73."""
     _target: Type = field(default_factory=lambda: GaussCtrlPipeline)
-    datamanager: Any = None
+    datamanager: GaussCtrlDataManagerConfig = field(default_factory=GaussCtrlDataManagerConfig)
     render_rate: int = 500
     edit_prompt: str = ""
     reverse_prompt: str = ""
@@ -76,7 +84,23 @@ class GaussCtrlPipelineConfig(VanillaPipelineConfig):
     edit_schedule: str = "refs_once"      # or "reference": refs recomputed in every chunk, as gc_pipeline.py:190-219
     view_batch: int = 40                  # views denoised per launch in the refs_once schedule; results do not depend on
                                           # it (batch-invariant kernels), throughput does (12 -> 40: +3 % on one B200)
-    synthetic_seed: int = 0               # weights seed when diffusion_ckpt is not a local checkpoint directory
+    synthetic_seed: int = 0               # weights seed for diffusion_ckpt="synthetic" (benchmarks / tests only)
+
+
+def resolve_checkpoint(ckpt: str) -> str:
+    """`from_pretrained(ckpt)` semantics without network (gc_pipeline.py:97-102): a local diffusers-layout folder, or a
+    hub id already present in the local Hugging Face cache.  Anything else raises - like the reference does when
+    `from_pretrained` cannot resolve the checkpoint - instead of silently editing with random weights."""
+    if os.path.isdir(ckpt):
+        return ckpt
+    try:
+        from huggingface_hub import snapshot_download  # local cache only: there is no network on the GPU box
+        return snapshot_download(ckpt, local_files_only=True)
+    except Exception as exc:
+        raise FileNotFoundError(
+            f"diffusion_ckpt={ckpt!r} is neither a local diffusers checkpoint folder nor in the local Hugging Face cache "
+            f"({type(exc).__name__}); pass a folder, or diffusion_ckpt='synthetic' for seeded random weights "
+            f"(benchmarks / tests only)") from exc
 
 
 class GaussCtrlPipeline(VanillaPipeline):
@@ -86,28 +110,37 @@ class GaussCtrlPipeline(VanillaPipeline):
                  local_rank: int = 0, grad_scaler: Optional[Any] = None, *, datamanager: Any = None, model: Any = None,
                  weights: Optional[tuple] = None, prompt_encoder: Optional[Callable] = None,
                  mask_fn: Optional[Callable] = None):
-        super().__init__(config, device, test_mode, world_size, local_rank)
-        if not HAVE_NERFSTUDIO:
-            self.datamanager = datamanager if datamanager is not None else config.datamanager
-            self._model = model
+        if datamanager is not None or model is not None:
+            # B200 extension (bench.py, tests): pre-built datamanager / model objects instead of building them from
+            # `config.datamanager` / `config.model` - the pipeline-specific state below is identical
+            torch.nn.Module.__init__(self)
+            self.config, self.test_mode, self.world_size = config, test_mode, world_size
+            self.datamanager, self._model = datamanager, model
+        else:
+            super().__init__(config, device, test_mode, world_size, local_rank)   # gc_pipeline.py:89
         self.config = config
         self.device_ = torch.device(device)
         self.test_mode = test_mode
         self.world_size, self.local_rank = world_size, local_rank
-        self.mask_fn = mask_fn  # LangSAM stays external: any callable rgb[H,W,3] -> mask[H,W]
+        self.mask_fn = mask_fn  # LangSAM stays external: any callable (rgb[H,W,3], text) -> mask[H,W]
         self.edit_prompt = config.edit_prompt
         self.reverse_prompt = config.reverse_prompt
         self.pipe_device = self.device_
+        ckpt_dir = None
         if weights is None:
-            weights = self._load_weights(config.diffusion_ckpt, config.synthetic_seed)
+            weights, ckpt_dir = self._load_weights(config.diffusion_ckpt, config.synthetic_seed)
         unet_sd, cnet_sd, vae_sd = weights
         self.denoiser = SD15Denoiser(unet_sd, cnet_sd, self.device_)
         self.vae = VaeB200(vae_sd, self.device_) if vae_sd is not None else None
         self.tables = DDIMTables()
         self.engine = EditEngine(self.denoiser, self.tables)
-        if prompt_encoder is None and os.path.isdir(config.diffusion_ckpt):
+        if prompt_encoder is None and ckpt_dir is not None:
             from .clip_text import make_prompt_encoder   # real tokenizer + CLIP text encoder on the B200 kernels
-            prompt_encoder = make_prompt_encoder(config.diffusion_ckpt, self.device_)
+            prompt_encoder = make_prompt_encoder(ckpt_dir, self.device_)
+            if prompt_encoder is None:
+                raise FileNotFoundError(f"{ckpt_dir}: tokenizer/ or text_encoder/ is missing - real UNet weights need the "
+                                        f"real prompt embeddings (the reference's from_pretrained would fail here too)")
+        # synthetic prompt embeddings only ever pair with synthetic / injected weights
         self.prompt_encoder = prompt_encoder or synthetic_prompt_embeds
         self.positive_prompt = self.edit_prompt + ", " + ADDED_PROMPT
         self.positive_reverse_prompt = self.reverse_prompt + ", " + ADDED_PROMPT
@@ -123,48 +156,132 @@ class GaussCtrlPipeline(VanillaPipeline):
 
     @staticmethod
     def _load_weights(ckpt: str, seed: int):
-        """A local diffusers-layout folder is loaded (checkpoint.py); a hub name such as the default
-        "CompVis/stable-diffusion-v1-4" cannot be resolved without network: seeded synthetic weights stand in."""
-        if os.path.isdir(ckpt):
-            from .checkpoint import load_diffusers_checkpoint
-            return load_diffusers_checkpoint(ckpt)
-        return synthetic_weights(seed)
+        """-> ((unet_sd, controlnet_sd, vae_sd), checkpoint folder or None).  `diffusion_ckpt="synthetic"` (optionally
+        "synthetic:<seed>") asks for seeded random-init weights explicitly; every other value must resolve to a
+        diffusers-layout folder (checkpoint.py) or raises."""
+        if ckpt == "synthetic" or ckpt.startswith("synthetic:"):
+            if ":" in ckpt:
+                seed = int(ckpt.split(":", 1)[1])
+            return synthetic_weights(seed), None
+        folder = resolve_checkpoint(ckpt)
+        from .checkpoint import load_diffusers_checkpoint
+        return load_diffusers_checkpoint(folder), folder
+
+    # ------------------------------------------------------------------------------------------ multi-GPU helpers
+    def _dist(self):
+        """(world, rank) of the view sharding: one process per GPU under torch.distributed, else (1, 0)."""
+        if self.world_size > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size(), torch.distributed.get_rank()
+        return 1, 0
+
+    def _camera_at(self, idx: int):
+        cam = self.datamanager.cameras[idx]
+        if len(cam.shape) == 0:           # nerfstudio Cameras[int] drops the batch dimension
+            cam = cam.reshape((1,))
+        return cam.to(self.device_)
 
     # ------------------------------------------------------------------------------------------ stage A
     @torch.no_grad()
     def render_reverse(self):
         """Render rgb + depth of every view, encode, and DDIM-invert to z_T (gc_pipeline.py:122-157).
-        The reference loops views at batch 1; here the three stages each run over all views in batches."""
-        cams = self.datamanager.cameras
-        V = len(cams)
+        The reference loops views at batch 1 on one GPU; here the three stages each run over a rank's views in batches,
+        views are dealt round-robin to the ranks (no collective on the data path) and ONE
+        all-gather at the end gives every rank the complete `train_data` (z_T 64 KB, render 2 MB per view)."""
+        V = len(self.datamanager.cameras)
+        world, rank = self._dist()
+        mine = list(range(rank, V, world))
+        want_mask = self.config.langsam_obj != ""
+        if want_mask and self.mask_fn is None:
+            raise ValueError(f"langsam_obj={self.config.langsam_obj!r} needs a segmentation callable: pass mask_fn=(rgb, "
+                             f"text) -> [H,W] mask (LangSAM in the reference, gc_pipeline.py:147-154)")
+        model = self.model
         rgbs, depths = [], []
-        for cam_idx in range(V):
-            out = self._model.get_outputs_for_camera(cams[cam_idx].to(self.device_))
+        for cam_idx in mine:
+            out = model.get_outputs_for_camera(self._camera_at(cam_idx))
             rgbs.append(out["rgb"].to(torch.float16))          # [H,W,3] 0..1   (:132)
             depths.append(out["depth"].to(torch.float16))      # [H,W,1]        (:133)
-        rgb = torch.stack(rgbs)
-        depth = torch.stack(depths)
-        z0 = torch.cat([self.image2latent_batch(rgb[i:i + 4]) for i in range(0, V, 4)])
-        disparity = ops.depth_to_disparity(depth[..., 0].float().contiguous(), True)   # depth2disparity_torch on fp16
-        disparity = ops.nhwc_to_nchw(disparity)
-        emb = self.prompt_encoder([self.positive_reverse_prompt])
-        zT = self.engine.invert(z0, disparity, emb, self.num_inference_steps)
-        for cam_idx in range(V):
-            mask = None
-            if self.config.langsam_obj != "" and self.mask_fn is not None:
-                mask = np.asarray(self.mask_fn(rgb[cam_idx].cpu(), self.config.langsam_obj)) * 1
-            self.update_datasets(cam_idx, rgb[cam_idx].cpu(), depth[cam_idx], zT[cam_idx:cam_idx + 1], mask)
+        H, W = (rgbs[0].shape[0], rgbs[0].shape[1]) if rgbs else (0, 0)
+        if mine:
+            rgb = torch.stack(rgbs)
+            depth = torch.stack(depths)
+            eb = self.stage_a_batch
+            z0 = torch.cat([self.image2latent_batch(rgb[i:i + eb]) for i in range(0, len(mine), eb)])
+            disparity = ops.depth_to_disparity(depth[..., 0].float().contiguous(), True)  # depth2disparity_torch on fp16
+            disparity = ops.nhwc_to_nchw(disparity)
+            emb = self.prompt_encoder([self.positive_reverse_prompt])
+            zT = self.engine.invert(z0, disparity, emb, self.num_inference_steps, batch=self.invert_batch)
+        masks = None
+        if want_mask:
+            masks = [np.asarray(self.mask_fn(rgbs[j].cpu(), self.config.langsam_obj)) * 1 for j in range(len(mine))]
+        if world > 1:
+            from . import parallel as par
+            shapes = par.broadcast_shape((H, W), self.device_)     # ranks without views still take part in the gather
+            H, W = shapes
+            e = lambda *shp, dt=torch.float16: torch.zeros(shp, dtype=dt, device=self.device_)  # noqa: E731
+            if not mine:
+                rgb, depth, zT = e(0, H, W, 3), e(0, H, W, 1), e(0, 4, H // 8, W // 8)
+            rgb = par.gather_view_results(rgb, mine, V, world)
+            depth = par.gather_view_results(depth, mine, V, world)
+            zT = par.gather_view_results(zT, mine, V, world)
+            if want_mask:
+                m_loc = torch.from_numpy(np.stack(masks).astype(np.int32)).to(self.device_) if mine else \
+                    e(0, H, W, dt=torch.int32)
+                m_all = par.gather_view_results(m_loc, mine, V, world).cpu().numpy()
+                masks = [m_all[i].astype(np.int64) for i in range(V)]
+            ids = list(range(V))
+        else:
+            ids = mine
+        # one device->host copy per product instead of the reference's three `.cpu()` syncs per view (:268-274)
+        rgb_h, depth_h, z_h = rgb.cpu(), depth.permute(0, 3, 1, 2).to(torch.float32).cpu(), zT.to(torch.float32).cpu()
+        for j, cam_idx in enumerate(ids):
+            self._store_view(cam_idx, rgb_h[j].clone(), depth_h[j].numpy().copy(), z_h[j:j + 1].numpy().copy(),
+                             None if masks is None else masks[j])
+
+    # batch sizes of stage A (B200 extension; results do not depend on them: batch-invariant kernels)
+    stage_a_batch = 8    # views per VAE-encode launch set (512^2 x 128-channel activations: 67 MB per view and layer)
+    invert_batch = 40    # views per DDIM-inversion launch set (the edit stage's view batch)
+
+    def _store_view(self, cam_idx, unedited_image, depth_np, latent_np, mask):
+        td = self.datamanager.train_data[cam_idx]
+        td["unedited_image"] = unedited_image
+        td["depth_image"] = depth_np
+        td["z_0_image"] = latent_np
+        if mask is not None:
+            td["mask_image"] = mask
 
     # ------------------------------------------------------------------------------------------ stage B
     @torch.no_grad()
     def edit_images(self):
         """Edit every view with ControlNet + cross-view attention and write the result into
-        `train_data[i]["image"]` as [H,W,3] fp32 on the CPU (gc_pipeline.py:159-237)."""
+        `train_data[i]["image"]` as [H,W,3] fp32 on the CPU (gc_pipeline.py:159-237).
+        With world_size > 1 the non-reference views are dealt round-robin to the ranks, every rank uploads only its own
+        views + the references, the reference pass is sharded over its CFG rows (parallel.py), each reference view is
+        decoded by one rank, and the decoded images are all-gathered so EVERY rank's train_data is complete (the
+        fine-tune that follows samples any view on any rank)."""
         td = self.datamanager.train_data
         V = len(td)
         dev = self.device_
-        z = torch.from_numpy(np.concatenate([d["z_0_image"] for d in td], axis=0)).pin_memory()
-        dep = torch.from_numpy(np.concatenate([d["depth_image"] for d in td], axis=0)).pin_memory()
+        S, g = self.num_inference_steps, float(self.guidance_scale)
+        if g <= 1.0:
+            # diffusers does not double the batch for CFG then, and CrossViewAttnProcessor's `video_length = B // 2`
+            # (utils.py:94) silently mixes views: every shipped script uses g in {3, 5, 7.5} (SURVEY §8a gotcha 2)
+            raise ValueError(f"guidance_scale={g} <= 1: the cross-view attention layout needs classifier-free guidance")
+        world, rank = self._dist()
+        refs = list(self.ref_indices)
+        R = self.num_ref_views
+        reference_schedule = self.config.edit_schedule == "reference"
+        if world > 1 and reference_schedule:
+            raise ValueError("edit_schedule='reference' is the single-GPU literal schedule; multi-GPU runs use 'refs_once'")
+        from . import parallel as par
+        if world > 1:
+            view_ids = par.shard_views(V, world, rank, refs)
+            mine = sorted(view_ids + [refs[i] for i in par.ref_decode_owner(R, world, rank)])
+        else:
+            view_ids, mine = None, list(range(V))
+        need = list(range(V)) if world == 1 else sorted(set(mine) | set(refs))   # views this rank uploads
+        pos_of = {v: j for j, v in enumerate(need)}
+        z = _pinned(torch.from_numpy(np.concatenate([td[i]["z_0_image"] for i in need], axis=0)))
+        dep = _pinned(torch.from_numpy(np.concatenate([td[i]["depth_image"] for i in need], axis=0)))
         z_dev = z.to(dev, non_blocking=True).to(torch.float16)
         dep_dev = dep.to(dev, non_blocking=True)
         self.h2d_bytes = z.numel() * 4 + dep.numel() * 4
@@ -172,48 +289,41 @@ class GaussCtrlPipeline(VanillaPipeline):
         disparity = ops.nhwc_to_nchw(ops.depth_to_disparity(dep_dev.contiguous(), False))
         emb = self.prompt_encoder([self.negative_prompts, self.positive_prompt])
         neg, pos = emb[0:1], emb[1:2]
-        S, g = self.num_inference_steps, float(self.guidance_scale)
-        if g <= 1.0:
-            # diffusers does not double the batch for CFG then, and CrossViewAttnProcessor's `video_length = B // 2`
-            # (utils.py:94) silently mixes views: every shipped script uses g in {3, 5, 7.5} (SURVEY §8a gotcha 2)
-            raise ValueError(f"guidance_scale={g} <= 1: the cross-view attention layout needs classifier-free guidance")
-        if self.config.edit_schedule == "reference":
-            R = self.num_ref_views
+        if reference_schedule:
             outs = []
             for i in range(0, V, self.chunk_size):
-                sel = list(self.ref_indices) + list(range(i, min(V, i + self.chunk_size)))
+                sel = refs + list(range(i, min(V, i + self.chunk_size)))
                 outs.append(self.engine.edit_reference_schedule(z_dev[sel], disparity[sel], pos, neg, S, g, R,
                                                                 ref_frames=crossview_ref_frames(R)))
             lat = torch.cat(outs)
-            mine = list(range(V))
         else:
-            dist_ctx, view_ids = None, None
-            mine = list(range(V))
-            if self.world_size > 1:
-                # views shard across ranks, the reference pass shards over its CFG rows (parallel.py); every rank
-                # writes the views it owns into its own train_data, rank 0 also the reference views
-                from . import parallel as par
+            dist_ctx = None
+            if world > 1:
                 if getattr(self, "_kv_gather", None) is None:
-                    self._kv_gather = par.KVAllGather()
-                rank = torch.distributed.get_rank()
-                dist_ctx = {"world": self.world_size, "rank": rank, "gather": self._kv_gather}
-                view_ids = par.shard_views(V, self.world_size, rank, self.ref_indices)
-                mine = sorted(view_ids + (list(self.ref_indices) if rank == 0 else []))
-            lat = self.engine.edit_refs_once(z_dev, disparity, self.ref_indices, pos, neg, S, g,
-                                             view_batch=max(1, getattr(self, "view_batch", getattr(self.config, "view_batch", self.chunk_size))), view_ids=view_ids,
-                                             dist_ctx=dist_ctx, ref_frames=crossview_ref_frames(self.num_ref_views))
+                    self._kv_gather = par.make_kv_gather(dev)
+                dist_ctx = {"world": world, "rank": rank, "gather": self._kv_gather}
+            vb = max(1, getattr(self, "view_batch", getattr(self.config, "view_batch", self.chunk_size)))
+            lat = self.engine.edit_refs_once(z_dev, disparity, [pos_of[r] for r in refs], pos, neg, S, g, view_batch=vb,
+                                             view_ids=None if view_ids is None else [pos_of[v] for v in view_ids],
+                                             dist_ctx=dist_ctx, ref_frames=crossview_ref_frames(R))
         masks = uned = None
         if all("mask_image" in td[i] for i in mine):
             masks = torch.from_numpy(np.stack([np.asarray(td[i]["mask_image"], dtype=np.float32) for i in mine])).to(dev)
             uned = torch.stack([td[i]["unedited_image"] for i in mine]).to(dev, torch.float16)
             self.h2d_bytes += masks.numel() * 4 + uned.numel() * 2
-        imgs = self.vae.decode_latents(lat[mine], masks, uned)         # [n,H,W,3] fp32
-        host = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=True)
+        imgs = self.vae.decode_latents(lat[[pos_of[i] for i in mine]], masks, uned)         # [n,H,W,3] fp32
+        ids = mine
+        if world > 1:
+            imgs = par.gather_view_results(imgs, mine, V, world)    # every rank ends up with all V edited images
+            ids = list(range(V))
+        host = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=imgs.is_cuda)
         host.copy_(imgs, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if imgs.is_cuda:
+            torch.cuda.current_stream().synchronize()
         self.d2h_bytes = host.numel() * 4
-        for j, i in enumerate(mine):
-            td[int(td[i].get("image_idx", i))]["image"] = host[j]   # global_idx = image_idx (gc_pipeline.py:224,234)
+        for j, i in enumerate(ids):
+            # global_idx = image_idx (gc_pipeline.py:224,234); own storage per view: the datamanager deep-copies entries
+            td[int(td[i].get("image_idx", i))]["image"] = host[j].clone()
 
     # ------------------------------------------------------------------------------------------ helpers (same names)
     @torch.no_grad()
@@ -238,13 +348,9 @@ class GaussCtrlPipeline(VanillaPipeline):
         return out.to(depth.dtype)
 
     def update_datasets(self, cam_idx, unedited_image, depth, latent, mask):
-        """gc_pipeline.py:268-274."""
-        td = self.datamanager.train_data[cam_idx]
-        td["unedited_image"] = unedited_image
-        td["depth_image"] = depth.permute(2, 0, 1).cpu().to(torch.float32).numpy()
-        td["z_0_image"] = latent.cpu().to(torch.float32).numpy()
-        if mask is not None:
-            td["mask_image"] = mask
+        """gc_pipeline.py:268-274 (same signature: depth [H,W,1] tensor, latent [1,4,h,w] tensor)."""
+        self._store_view(cam_idx, unedited_image, depth.permute(2, 0, 1).cpu().to(torch.float32).numpy(),
+                         latent.cpu().to(torch.float32).numpy(), mask)
 
     # ---- B200 extension: stage-A products on disk in the reference's folder layout (store.py, SURVEY §8f row 3)
     def save_stage_a(self, root: str) -> None:
@@ -261,7 +367,7 @@ class GaussCtrlPipeline(VanillaPipeline):
 
     def get_train_loss_dict(self, step: int):
         ray_bundle, batch = self.datamanager.next_train(step)
-        model_outputs = self._model(ray_bundle)
+        model_outputs = self._model(ray_bundle)  # gc_pipeline.py:276-287
         metrics_dict = self.model.get_metrics_dict(model_outputs, batch)
         loss_dict = self.model.get_loss_dict(model_outputs, batch, metrics_dict)
         return model_outputs, loss_dict, metrics_dict

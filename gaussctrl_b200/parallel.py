@@ -25,6 +25,26 @@ def shard_views(V: int, world: int, rank: int, ref_indices: Sequence[int]) -> Li
     return non_ref[rank::world]
 
 
+def ref_decode_owner(R: int, world: int, rank: int) -> List[int]:
+    """Which of the R reference views (positions in `ref_indices`) this rank decodes and reports.  Every rank holds all R
+    reference latents after the reference pass, so any rank can; they are dealt from the LAST rank downwards because
+    `shard_views` gives the low ranks the extra non-reference views."""
+    return [i for i in range(R) if (world - 1 - i) % world == rank]
+
+
+def broadcast_shape(shape: Sequence[int], device, group: Optional[dist.ProcessGroup] = None) -> Tuple[int, ...]:
+    """Element-wise maximum of a small integer tuple over the ranks (a rank without views does not know the image
+    size; it still has to take part in the gathers with correctly shaped empty contributions)."""
+    t = torch.tensor(list(shape), dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return tuple(int(v) for v in t.tolist())
+
+
+def make_kv_gather(device, group: Optional[dist.ProcessGroup] = None):
+    """The reference-K/V exchange of this process group: NCCL all-gather (KVAllGather)."""
+    return KVAllGather(group)
+
+
 def ref_row_partition(R: int, world: int, rank: int) -> List[int]:
     """Global CFG-row ids (0..2R-1, layout [uncond x R | cond x R]) of the reference pass owned by `rank`.
     Rows are dealt contiguously; when world > 2R the extra ranks own no reference row (they still take part in the
