@@ -54,11 +54,10 @@ SIGNATURES = {
     "gcb_sh_fwd": (c_int, [c_int, c_int, _P, _P, _P, c_int, _P]),
     "gcb_scan_workspace_bytes": (c_size_t, [c_int]),
     "gcb_cumsum_i32": (c_int, [_P, _P, c_int, _P, c_size_t, _P]),
-    "gcb_depth_order_workspace_bytes": (c_size_t, [c_int]),
-    "gcb_depth_order": (c_int, [_P, _P, c_int, _P, _P, _P, c_size_t, _P]),
-    "gcb_bin_tiles_workspace_bytes": (c_size_t, [c_int, c_longlong, c_int, c_int]),
-    "gcb_bin_tiles": (c_int, [_P, _P, _P, _P, _P, c_int, c_longlong, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
-    "gcb_rasterize_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _FP, _P, _P, _P, _P]),
+    "gcb_bin_gaussians_workspace_bytes": (c_size_t, [c_int, c_longlong, c_int, c_int]),
+    "gcb_bin_gaussians": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_longlong, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "gcb_rasterize_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _FP, _P, _P, _P, _P]),
+    "gcb_rasterize_rgbd_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "gcb_rasterize_bwd": (c_int, [_P] * 6 + [c_int, c_int, c_int, _FP] + [_P] * 8 + [_P]),
     "gcb_project_gaussians_bwd": (c_int, [_P, _P, c_float, _P, _FP, _FP, c_float, c_float, c_float, c_float, c_int, c_int,
                                           _P, _P, _P, _P, c_int, _P, _P, _P, _P]),

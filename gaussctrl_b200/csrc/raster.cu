@@ -2,10 +2,7 @@
 // Replaces gsplat 0.1.3's CUDA extension behind gc_model.py:140-154 (project_gaussians), :166 (spherical_harmonics),
 // :174-186 and :191-202 (rasterize_gaussians).  fp32 SIMT, HBM/L2-bound.
 //
-// Binning is NOT gsplat's "sort M 64-bit (tile|depth) keys": the Gaussians (N) are ordered by depth once
-// (3 stable radix passes of 11+11+10 bits over N 32-bit keys), intersections (M ~ 10 N) are emitted in that order and
-// ONE stable 10-bit radix pass by tile id groups them.  The result is identical to a stable sort by
-// (tile << 32 | depth bits) with ties by Gaussian id - the order the oracle defines - at a fraction of the traffic.
+// Tile binning (depth order, intersections, tile runs) lives in raster_bin.cu.
 //
 // Every fp32 expression of the projection kernel is an explicit tree of single IEEE operations (__fmul_rn /
 // __fadd_rn, never contracted to FMA) mirroring oracle/gsplat_ref.py so the result is bit-exact.
@@ -271,278 +268,36 @@ __global__ void __launch_bounds__(256) project_sh_fused_kernel(
     opac[i] = 1.f / (1.f + expf(-opac_logit[i]));
 }
 
-// ------------------------------------------------------------------------------------------ scan (int32)
-constexpr int SCAN_T = 1024, SCAN_IPT = 4, SCAN_CHUNK = SCAN_T * SCAN_IPT;
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += n;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
-        int wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += n;
-        }
-        s_warp[lane] = wi - w;
-        if (lane == 31) s_warp[32] = wi;
-    }
-    __syncthreads();
-    total = s_warp[32];
-    const int r = s_warp[warp] + inc - v;
-    __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(SCAN_T) scan_reduce_kernel(const int* __restrict__ in, int* __restrict__ sums,
-                                                             long long n) {
-    __shared__ int s_warp[33];
-    const long long base = (long long)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
-    int v = 0;
-#pragma unroll
-    for (int j = 0; j < SCAN_IPT; ++j)
-        if (base + j < n) v += in[base + j];
-    int total;
-    block_exclusive_scan(v, s_warp, total);
-    if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-
-// out = scan(in) + offsets[block] ; inclusive != 0 -> inclusive scan
-__global__ void __launch_bounds__(SCAN_T) scan_apply_kernel(const int* __restrict__ in, const int* __restrict__ offsets,
-                                                            int* __restrict__ out, long long n, int inclusive) {
-    __shared__ int s_warp[33];
-    const long long base = (long long)blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
-    int x[SCAN_IPT];
-    int v = 0;
-#pragma unroll
-    for (int j = 0; j < SCAN_IPT; ++j) {
-        x[j] = base + j < n ? in[base + j] : 0;
-        v += x[j];
-    }
-    int total;
-    int run = block_exclusive_scan(v, s_warp, total) + (offsets ? offsets[blockIdx.x] : 0);
-#pragma unroll
-    for (int j = 0; j < SCAN_IPT; ++j) {
-        if (base + j < n) out[base + j] = inclusive ? run + x[j] : run;
-        run += x[j];
-    }
-}
-
-// single block, sequential over chunks: exclusive scan in place (n small)
-__global__ void __launch_bounds__(SCAN_T) scan_small_kernel(int* __restrict__ data, int n) {
-    __shared__ int s_warp[33];
-    int carry = 0;
-    for (int c0 = 0; c0 < n; c0 += SCAN_T) {
-        const int i = c0 + threadIdx.x;
-        const int v = i < n ? data[i] : 0;
-        int total;
-        const int ex = block_exclusive_scan(v, s_warp, total);
-        if (i < n) data[i] = carry + ex;
-        carry += total;
-    }
-}
-
-size_t scan_ws_ints(long long n) {
-    const long long l0 = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
-    const long long l1 = (l0 + SCAN_CHUNK - 1) / SCAN_CHUNK;
-    return (size_t)(l0 + l1 + 64);
-}
-
-// scan `in` (n ints) to `out` (may alias), exclusive or inclusive
-int scan_i32(const int* in, int* out, long long n, int inclusive, int* ws, cudaStream_t st) {
-    if (n <= 0) return GCB_OK;
-    const long long l0 = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
-    const long long l1 = (l0 + SCAN_CHUNK - 1) / SCAN_CHUNK;
-    int* s0 = ws;
-    int* s1 = ws + l0;
-    scan_reduce_kernel<<<(unsigned)l0, SCAN_T, 0, st>>>(in, s0, n);
-    if (l0 > SCAN_CHUNK) {
-        scan_reduce_kernel<<<(unsigned)l1, SCAN_T, 0, st>>>(s0, s1, l0);
-        scan_small_kernel<<<1, SCAN_T, 0, st>>>(s1, (int)l1);
-        scan_apply_kernel<<<(unsigned)l1, SCAN_T, 0, st>>>(s0, s1, s0, l0, 0);
-    } else {
-        scan_small_kernel<<<1, SCAN_T, 0, st>>>(s0, (int)l0);
-    }
-    scan_apply_kernel<<<(unsigned)l0, SCAN_T, 0, st>>>(in, s0, out, n, inclusive);
-    GCB_LAUNCH_CHECK();
-    return GCB_OK;
-}
-
-// ------------------------------------------------------------------------------------------ stable radix pass
-// Block = 8 warps x 8 batches x 32 keys = 2048 keys.  Histogram kernel: shared-memory atomics (order irrelevant).
-// Scatter kernel: ONE traversal - keys stay in registers, each key records (same-digit keys seen earlier by its warp)
-// + (rank among equal digits inside its 32-key batch, __match_any_sync); after the block-wide exclusive bases are
-// known the final position is base[warp][digit] + local rank.  Stable by construction (block, warp, batch, lane).
-constexpr int RP_WARPS = 8, RP_BATCHES = 8, RP_PER_WARP = RP_BATCHES * 32, RP_PER_BLOCK = RP_WARPS * RP_PER_WARP;
-constexpr int RP_MAX_BINS = 2048;
-
-__global__ void __launch_bounds__(256) rp_hist_kernel(const uint32_t* __restrict__ keys, long long n, int shift,
-                                                      int bins, int* __restrict__ counts) {
-    extern __shared__ int s_cnt[];  // [bins]
-    for (int i = threadIdx.x; i < bins; i += 256) s_cnt[i] = 0;
-    __syncthreads();
-    const uint32_t mask = (uint32_t)bins - 1;
-    const long long b0 = (long long)blockIdx.x * RP_PER_BLOCK;
-#pragma unroll
-    for (int it = 0; it < RP_PER_BLOCK / 256; ++it) {
-        const long long i = b0 + it * 256 + threadIdx.x;
-        if (i < n) atomicAdd(&s_cnt[(keys[i] >> shift) & mask], 1);
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < bins; b += 256) counts[(long long)b * gridDim.x + blockIdx.x] = s_cnt[b];
-}
-
-__global__ void __launch_bounds__(256) rp_scatter_kernel(const uint32_t* __restrict__ keys,
-                                                         const int32_t* __restrict__ vals, long long n, int shift,
-                                                         int bins, const int* __restrict__ offsets,
-                                                         uint32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out) {
-    extern __shared__ int s_cnt[];  // [RP_WARPS][bins]: per-warp digit counts, then running write bases
-    for (int i = threadIdx.x; i < RP_WARPS * bins; i += 256) s_cnt[i] = 0;
-    __syncthreads();
-    const uint32_t mask = (uint32_t)bins - 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* cnt_w = s_cnt + warp * bins;
-    const long long w0 = (long long)blockIdx.x * RP_PER_BLOCK + (long long)warp * RP_PER_WARP;
-    uint32_t key[RP_BATCHES];
-    int32_t val[RP_BATCHES];
-    int lrank[RP_BATCHES];
-#pragma unroll
-    for (int it = 0; it < RP_BATCHES; ++it) {
-        const long long i = w0 + it * 32 + lane;
-        const bool act = i < n;
-        const unsigned am = __ballot_sync(0xffffffffu, act);
-        lrank[it] = -1;
-        if (act) {
-            key[it] = keys[i];
-            val[it] = vals ? vals[i] : (int32_t)i;
-            const uint32_t bin = (key[it] >> shift) & mask;
-            const unsigned peers = __match_any_sync(am, bin);
-            const int rank = __popc(peers & ((1u << lane) - 1));
-            const int prior = cnt_w[bin];
-            __syncwarp(am);
-            if (rank == 0) cnt_w[bin] = prior + __popc(peers);
-            lrank[it] = prior + rank;
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < bins; b += 256) {
-        int run = offsets[(long long)b * gridDim.x + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < RP_WARPS; ++w) {
-            const int c = s_cnt[w * bins + b];
-            s_cnt[w * bins + b] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < RP_BATCHES; ++it) {
-        if (lrank[it] >= 0) {
-            const int pos = cnt_w[(key[it] >> shift) & mask] + lrank[it];
-            if (keys_out) keys_out[pos] = key[it];
-            vals_out[pos] = val[it];
-        }
-    }
-}
-
-inline long long rp_blocks(long long n) { return (n + RP_PER_BLOCK - 1) / RP_PER_BLOCK; }
-
-// one stable pass; ws_counts must hold bins * blocks ints followed by scan workspace
-int radix_pass(const uint32_t* keys, const int32_t* vals, long long n, int shift, int bits, uint32_t* keys_out,
-               int32_t* vals_out, int* ws, cudaStream_t st) {
-    const int bins = 1 << bits;
-    const long long nb = rp_blocks(n);
-    const size_t smem = (size_t)RP_WARPS * bins * sizeof(int);
-    static bool configured = false;
-    if (!configured) {
-        GCB_CUDA(cudaFuncSetAttribute(rp_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      RP_WARPS * RP_MAX_BINS * (int)sizeof(int)));
-        configured = true;
-    }
-    int* counts = ws;
-    int* scan_ws = ws + (long long)bins * nb;
-    rp_hist_kernel<<<(unsigned)nb, 256, (size_t)bins * sizeof(int), st>>>(keys, n, shift, bins, counts);
-    int rc = scan_i32(counts, counts, (long long)bins * nb, 0, scan_ws, st);
-    if (rc != GCB_OK) return rc;
-    rp_scatter_kernel<<<(unsigned)nb, 256, smem, st>>>(keys, vals, n, shift, bins, counts, keys_out, vals_out);
-    GCB_LAUNCH_CHECK();
-    return GCB_OK;
-}
-
-size_t radix_ws_ints(long long n, int bits) {
-    const long long cnt = (long long)(1 << bits) * rp_blocks(n);
-    return (size_t)cnt + scan_ws_ints(cnt);
-}
-
-__global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ idx,
-                                  int32_t* __restrict__ dst, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[idx[i]];
-}
-
-// emit intersections of the depth-ordered Gaussians: tile ids (as radix keys) and Gaussian ids
-__global__ void emit_isects_kernel(const float* __restrict__ xys, const int32_t* __restrict__ radii,
-                                   const int32_t* __restrict__ sorted_ids, const int32_t* __restrict__ cum_sorted, int N,
-                                   int tbx, int tby, uint32_t* __restrict__ tile_of, int32_t* __restrict__ gid_of) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int g = sorted_ids[i];
-    const int rad = radii[g];
-    if (rad <= 0) return;
-    int x0, x1, y0, y1;
-    tile_bbox(xys[2 * g], xys[2 * g + 1], (float)rad, tbx, tby, x0, x1, y0, y1);
-    long long cur = i > 0 ? cum_sorted[i - 1] : 0;
-    for (int ty = y0; ty < y1; ++ty)
-        for (int tx = x0; tx < x1; ++tx) {
-            tile_of[cur] = (uint32_t)(ty * tbx + tx);
-            gid_of[cur] = g;
-            ++cur;
-        }
-}
-
-__global__ void tile_bins_kernel(const uint32_t* __restrict__ tile_sorted, long long M, int32_t* __restrict__ bins) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    const uint32_t t = tile_sorted[i];
-    if (i == 0 || tile_sorted[i - 1] != t) bins[2 * t] = (int32_t)i;
-    if (i == M - 1 || tile_sorted[i + 1] != t) bins[2 * t + 1] = (int32_t)(i + 1);
-}
-
-__global__ void isect_keys_kernel(const uint32_t* __restrict__ tile_sorted, const int32_t* __restrict__ gids,
-                                  const float* __restrict__ depths, long long M, int64_t* __restrict__ keys) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    keys[i] = ((int64_t)tile_sorted[i] << 32) | (int64_t)(uint32_t)__float_as_uint(depths[gids[i]]);
-}
-
 // ------------------------------------------------------------------------------------------ compositing
-template <int C>
+// FUSED: C == 4 channels are (r, g, b, depth) and the get_outputs epilogue (gc_model.py:187-204) is applied in place:
+// out = rgb [H,W,3] clamped to <= 1, out_depth = depth / alpha (1000 where alpha == 0), out_alpha = 1 - T.
+template <int C, bool FUSED>
 __global__ void __launch_bounds__(256) rasterize_fwd_kernel(const float* __restrict__ xys,
                                                             const float* __restrict__ conics,
                                                             const float* __restrict__ colors,
                                                             const float* __restrict__ opac,
                                                             const int32_t* __restrict__ gids,
-                                                            const int32_t* __restrict__ bins, int H, int W, int tbx,
+                                                            const int32_t* __restrict__ bins,
+                                                            const int32_t* __restrict__ radii, int H, int W, int tbx,
                                                             float bg0, float bg1, float bg2, float bg3,
                                                             float* __restrict__ out, float* __restrict__ final_T,
-                                                            int32_t* __restrict__ final_idx) {
+                                                            int32_t* __restrict__ final_idx,
+                                                            float* __restrict__ out_depth,
+                                                            float* __restrict__ out_alpha,
+                                                            const float* __restrict__ d_bg) {
     __shared__ float4 s_xyo[256];   // x, y, opacity, conic.x
     __shared__ float2 s_con[256];   // conic.y, conic.z
+    __shared__ float s_thr[256];    // sigma above which alpha = o * exp(-sigma) is certainly < 1/255
+    __shared__ float s_r2[256];     // squared distance from the centre beyond which that holds for every pixel
     __shared__ float s_col[256 * C];
     const int tile = blockIdx.y * tbx + blockIdx.x;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int px_i = blockIdx.x * BLOCK + tx, py_i = blockIdx.y * BLOCK + ty;
+    // a warp owns an 8 x 4 pixel sub-block of the tile (compact, so whole Gaussians can be culled per warp)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sbx = blockIdx.x * BLOCK + (warp & 1) * 8, sby = blockIdx.y * BLOCK + (warp >> 1) * 4;
+    const int px_i = sbx + (lane & 7), py_i = sby + (lane >> 3);
     const bool inside = px_i < W && py_i < H;
     const float px = (float)px_i, py = (float)py_i;
+    const float rx0 = (float)sbx, rx1 = (float)(sbx + 7), ry0 = (float)sby, ry1 = (float)(sby + 3);
     const int start = bins[2 * tile], end = bins[2 * tile + 1];
     float T = 1.f;
     float acc[C];
@@ -556,25 +311,54 @@ __global__ void __launch_bounds__(256) rasterize_fwd_kernel(const float* __restr
         if (i < end) {
             const int g = gids[i];
             const float2 xy = reinterpret_cast<const float2*>(xys)[g];
-            s_xyo[threadIdx.x] = make_float4(xy.x, xy.y, opac[g], conics[3 * g]);
+            const float o = opac[g];
+            s_xyo[threadIdx.x] = make_float4(xy.x, xy.y, o, conics[3 * g]);
             s_con[threadIdx.x] = make_float2(conics[3 * g + 1], conics[3 * g + 2]);
+            // alpha < 1/255  <=>  sigma > ln(255 o); the margin (1e-3 relative in alpha) is four orders of magnitude above
+            // the rounding of expf / logf, so every pair skipped here would have failed the exact test below as well:
+            // results are bit-identical, the exponential is only evaluated near or inside the Gaussian's support
+            const float thr = logf(255.f * o) + 1e-3f;
+            s_thr[threadIdx.x] = thr;
+            // sigma >= 0.5 * lambda_min(conic) * d^2 and lambda_min(conic) = 1 / lambda_max(cov2d) >= 9 / radius^2
+            // (radius = ceil(3 sqrt(lambda_max)), project_one): beyond d^2 = thr * radius^2 / 4.5 no pixel passes the
+            // exact test, so a warp whose sub-block is farther away skips the Gaussian without evaluating it
+            float r2 = __int_as_float(0x7f800000);
+            if (radii) {
+                const float r = (float)radii[g];
+                r2 = thr > 0.f ? thr * r * r * (1.0001f / 4.5f) + 1e-3f : -1.f;
+            }
+            s_r2[threadIdx.x] = r2;
 #pragma unroll
             for (int c = 0; c < C; ++c) s_col[threadIdx.x * C + c] = colors[(long long)g * C + c];
         }
         __syncthreads();
         const int cnt = min(256, end - b0);
-        if (!done) {
-            for (int j = 0; j < cnt; ++j) {
+        for (int r0 = 0; r0 < cnt; r0 += 32) {
+            if (__all_sync(0xffffffffu, done)) break;
+            // which of these 32 Gaussians can touch this warp's sub-block at all (front-to-back order is kept below)
+            const int jt = r0 + lane;
+            bool hit = false;
+            if (jt < cnt) {
+                const float4 qt = s_xyo[jt];
+                const float ddx = fmaxf(fmaxf(rx0 - qt.x, qt.x - rx1), 0.f), ddy = fmaxf(fmaxf(ry0 - qt.y, qt.y - ry1), 0.f);
+                hit = !(ddx * ddx + ddy * ddy > s_r2[jt]);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = r0 + __ffs(m) - 1;
+                m &= m - 1;
+                if (done) continue;
                 const float4 q = s_xyo[j];
                 const float2 cc = s_con[j];
                 const float dx = q.x - px, dy = q.y - py;
                 const float sigma = 0.5f * (q.w * dx * dx + cc.y * dy * dy) + cc.x * dx * dy;
+                if (sigma > s_thr[j]) continue;
                 const float alpha = fminf(0.999f, q.z * expf(-sigma));
                 if (sigma < 0.f || alpha < (1.f / 255.f)) continue;
                 const float nT = T * (1.f - alpha);
                 if (nT <= 1e-4f) {
                     done = true;
-                    break;
+                    continue;
                 }
                 const float vis = alpha * T;
 #pragma unroll
@@ -586,11 +370,26 @@ __global__ void __launch_bounds__(256) rasterize_fwd_kernel(const float* __restr
     }
     if (inside) {
         const long long pid = (long long)py_i * W + px_i;
-        const float bg[4] = {bg0, bg1, bg2, bg3};
+        float bg[4] = {bg0, bg1, bg2, bg3};
+        if constexpr (FUSED) {
+            bg[0] = d_bg[0];
+            bg[1] = d_bg[1];
+            bg[2] = d_bg[2];
+            static_assert(C == 4, "fused rgb+depth epilogue needs (r, g, b, depth)");
+            const float a = 1.f - T;
+            out[pid * 3] = fminf(acc[0] + T * bg[0], 1.f);
+            out[pid * 3 + 1] = fminf(acc[1] + T * bg[1], 1.f);
+            out[pid * 3 + 2] = fminf(acc[2] + T * bg[2], 1.f);
+            out_depth[pid] = a > 0.f ? (acc[3] + T * bg[3]) / a : 1000.f;
+            out_alpha[pid] = a;
+            if (final_T) final_T[pid] = T;
+            if (final_idx) final_idx[pid] = last;
+        } else {
 #pragma unroll
-        for (int c = 0; c < C; ++c) out[pid * C + c] = acc[c] + T * bg[c];
-        final_T[pid] = T;
-        final_idx[pid] = last;
+            for (int c = 0; c < C; ++c) out[pid * C + c] = acc[c] + T * bg[c];
+            final_T[pid] = T;
+            final_idx[pid] = last;
+        }
     }
 }
 
@@ -700,100 +499,10 @@ extern "C" int gcb_sh_fwd(int degree, int K, const float* viewdirs, const float*
     return GCB_OK;
 }
 
-extern "C" size_t gcb_scan_workspace_bytes(int N) { return scan_ws_ints(N) * sizeof(int); }
-
-extern "C" int gcb_cumsum_i32(const int32_t* in, int32_t* out, int N, void* workspace, size_t workspace_bytes,
-                              void* stream) {
-    GCB_CHECK_ARG(in && out && workspace, "null pointer");
-    if (workspace_bytes < gcb_scan_workspace_bytes(N)) {
-        gcb_set_error("scan workspace too small");
-        return GCB_ERR_WORKSPACE;
-    }
-    return scan_i32(in, out, N, 1, (int*)workspace, ST);
-}
-
-// workspace layout of gcb_depth_order: keys A/B [N] u32, ids B [N] i32, nth_sorted [N] i32, radix/scan scratch
-extern "C" size_t gcb_depth_order_workspace_bytes(int N) {
-    return ((size_t)4 * N + radix_ws_ints(N, 11) + scan_ws_ints(N) + 64) * sizeof(int);
-}
-
-extern "C" int gcb_depth_order(const float* depths, const int32_t* num_tiles_hit, int N, int32_t* sorted_ids,
-                               int32_t* cum_sorted, void* workspace, size_t workspace_bytes, void* stream) {
-    GCB_CHECK_ARG(depths && num_tiles_hit && sorted_ids && cum_sorted && workspace, "null pointer");
-    GCB_CHECK_ARG(N > 0, "N must be positive");
-    if (workspace_bytes < gcb_depth_order_workspace_bytes(N)) {
-        gcb_set_error("depth-order workspace too small");
-        return GCB_ERR_WORKSPACE;
-    }
-    uint32_t* kA = (uint32_t*)workspace;
-    uint32_t* kB = kA + N;
-    int32_t* vB = (int32_t*)(kB + N);
-    int32_t* nth_sorted = vB + N;
-    int* scratch = (int*)(nth_sorted + N);
-    // depths are >= 0 so their bit patterns order like unsigned integers; 3 stable LSD passes of 11 + 11 + 10 bits
-    const uint32_t* dk = reinterpret_cast<const uint32_t*>(depths);
-    int rc;
-    if ((rc = radix_pass(dk, nullptr, N, 0, 11, kA, vB, scratch, ST))) return rc;
-    if ((rc = radix_pass(kA, vB, N, 11, 11, kB, sorted_ids, scratch, ST))) return rc;
-    if ((rc = radix_pass(kB, sorted_ids, N, 22, 10, nullptr, vB, scratch, ST))) return rc;
-    GCB_CUDA(cudaMemcpyAsync(sorted_ids, vB, (size_t)N * sizeof(int32_t), cudaMemcpyDeviceToDevice, ST));
-    gather_i32_kernel<<<gcb_cdiv(N, 256), 256, 0, ST>>>(num_tiles_hit, sorted_ids, nth_sorted, N);
-    return scan_i32(nth_sorted, cum_sorted, N, 1, scratch, ST);
-}
-
-extern "C" size_t gcb_bin_tiles_workspace_bytes(int N, long long M, int tile_bx, int tile_by) {
-    (void)N;
-    (void)tile_bx;
-    (void)tile_by;
-    return ((size_t)3 * M + radix_ws_ints(M, 11) + 64) * sizeof(int);
-}
-
-extern "C" int gcb_bin_tiles(const float* xys, const float* depths, const int32_t* radii, const int32_t* sorted_ids,
-                             const int32_t* cum_sorted, int N, long long M, int tile_bx, int tile_by,
-                             int32_t* gaussian_ids, int32_t* tile_bins, int64_t* isect_keys, void* workspace,
-                             size_t workspace_bytes, void* stream) {
-    GCB_CHECK_ARG(xys && radii && sorted_ids && cum_sorted && gaussian_ids && tile_bins && workspace, "null pointer");
-    GCB_CHECK_ARG(!isect_keys || depths, "isect_keys requested without depths");
-    const int ntiles = tile_bx * tile_by;
-    GCB_CHECK_ARG(ntiles > 0 && ntiles <= (1 << 20), "tile grid %dx%d unsupported", tile_bx, tile_by);
-    GCB_CHECK_ARG(M >= 0 && M < (1ll << 31), "M out of range");
-    GCB_CUDA(cudaMemsetAsync(tile_bins, 0, (size_t)ntiles * 2 * sizeof(int32_t), ST));
-    if (M == 0) return GCB_OK;
-    if (workspace_bytes < gcb_bin_tiles_workspace_bytes(N, M, tile_bx, tile_by)) {
-        gcb_set_error("bin-tiles workspace too small");
-        return GCB_ERR_WORKSPACE;
-    }
-    uint32_t* tA = (uint32_t*)workspace;
-    uint32_t* tB = tA + M;
-    int32_t* gA = (int32_t*)(tB + M);
-    int* scratch = (int*)(gA + M);
-    emit_isects_kernel<<<gcb_cdiv(N, 256), 256, 0, ST>>>(xys, radii, sorted_ids, cum_sorted, N, tile_bx, tile_by, tA, gA);
-    GCB_LAUNCH_CHECK();
-    int bits_total = 1;
-    while ((1 << bits_total) < ntiles) ++bits_total;
-    int rc;
-    const uint32_t* tile_sorted;
-    if (bits_total <= 11) {
-        if ((rc = radix_pass(tA, gA, M, 0, bits_total, tB, gaussian_ids, scratch, ST))) return rc;
-        tile_sorted = tB;
-    } else {
-        const int lo = bits_total / 2, hi = bits_total - lo;
-        if ((rc = radix_pass(tA, gA, M, 0, lo, tB, gaussian_ids, scratch, ST))) return rc;
-        if ((rc = radix_pass(tB, gaussian_ids, M, lo, hi, tA, gA, scratch, ST))) return rc;
-        GCB_CUDA(cudaMemcpyAsync(gaussian_ids, gA, (size_t)M * sizeof(int32_t), cudaMemcpyDeviceToDevice, ST));
-        tile_sorted = tA;
-    }
-    const unsigned nb = (unsigned)((M + 255) / 256);
-    tile_bins_kernel<<<nb, 256, 0, ST>>>(tile_sorted, M, tile_bins);
-    if (isect_keys) isect_keys_kernel<<<nb, 256, 0, ST>>>(tile_sorted, gaussian_ids, depths, M, isect_keys);
-    GCB_LAUNCH_CHECK();
-    return GCB_OK;
-}
-
 extern "C" int gcb_rasterize_fwd(const float* xys, const float* conics, const float* colors, const float* opacities,
-                                 const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
-                                 const float* h_background, float* out_img, float* final_T, int32_t* final_idx,
-                                 void* stream) {
+                                 const int32_t* gaussian_ids, const int32_t* tile_bins, const int32_t* radii, int img_h,
+                                 int img_w, int C, const float* h_background, float* out_img, float* final_T,
+                                 int32_t* final_idx, void* stream) {
     GCB_CHECK_ARG(xys && conics && colors && opacities && gaussian_ids && tile_bins, "null input");
     GCB_CHECK_ARG(out_img && final_T && final_idx && h_background, "null output/background");
     const int tbx = gcb_cdiv(img_w, BLOCK), tby = gcb_cdiv(img_h, BLOCK);
@@ -802,24 +511,39 @@ extern "C" int gcb_rasterize_fwd(const float* xys, const float* conics, const fl
     for (int c = 0; c < C && c < 4; ++c) bg[c] = h_background[c];
     switch (C) {
         case 1:
-            rasterize_fwd_kernel<1><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins, img_h,
-                                                          img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img, final_T,
-                                                          final_idx);
+            rasterize_fwd_kernel<1, false><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins,
+                                                                 radii, img_h, img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img,
+                                                                 final_T, final_idx, nullptr, nullptr, nullptr);
             break;
         case 3:
-            rasterize_fwd_kernel<3><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins, img_h,
-                                                          img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img, final_T,
-                                                          final_idx);
+            rasterize_fwd_kernel<3, false><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins,
+                                                                 radii, img_h, img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img,
+                                                                 final_T, final_idx, nullptr, nullptr, nullptr);
             break;
         case 4:
-            rasterize_fwd_kernel<4><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins, img_h,
-                                                          img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img, final_T,
-                                                          final_idx);
+            rasterize_fwd_kernel<4, false><<<grid, 256, 0, ST>>>(xys, conics, colors, opacities, gaussian_ids, tile_bins,
+                                                                 radii, img_h, img_w, tbx, bg[0], bg[1], bg[2], bg[3], out_img,
+                                                                 final_T, final_idx, nullptr, nullptr, nullptr);
             break;
         default:
             gcb_set_error("rasterize: C=%d not built (1, 3, 4)", C);
             return GCB_ERR_UNSUPPORTED;
     }
+    GCB_LAUNCH_CHECK();
+    return GCB_OK;
+}
+
+extern "C" int gcb_rasterize_rgbd_fwd(const float* xys, const float* conics, const float* rgbd, const float* opacities,
+                                      const int32_t* gaussian_ids, const int32_t* tile_bins, const int32_t* radii,
+                                      int img_h, int img_w, const float* d_background3, float* out_rgb, float* out_depth,
+                                      float* out_alpha, void* stream) {
+    GCB_CHECK_ARG(xys && conics && rgbd && opacities && gaussian_ids && tile_bins && d_background3, "null input");
+    GCB_CHECK_ARG(out_rgb && out_depth && out_alpha, "null output");
+    const int tbx = gcb_cdiv(img_w, BLOCK), tby = gcb_cdiv(img_h, BLOCK);
+    dim3 grid(tbx, tby);
+    rasterize_fwd_kernel<4, true><<<grid, 256, 0, ST>>>(xys, conics, rgbd, opacities, gaussian_ids, tile_bins, radii, img_h,
+                                                        img_w, tbx, 0.f, 0.f, 0.f, 0.f, out_rgb, nullptr, nullptr, out_depth,
+                                                        out_alpha, d_background3);
     GCB_LAUNCH_CHECK();
     return GCB_OK;
 }

@@ -54,11 +54,9 @@ def render_gaussians(params: Dict[str, torch.Tensor], c2w: torch.Tensor, fx, fy,
     if (not training and not torch.is_grad_enabled() and sh_degree_active >= 0 and params["features_rest"].shape[1] == 15
             and gsplat_ops.FUSED_EVAL):
         # eval path (render_reverse, ns-gaussctrl-render): fused front end on the raw parameters
-        res = gsplat_ops.render_eval_fused(params, vm, pm @ vm, c2w.detach().to("cpu", torch.float32)[:3, 3].tolist(),
-                                           fx, fy, cx, cy, H, W, sh_degree_active, background)
-        if res is None:
-            return {"rgb": background.repeat(H, W, 1)}
-        rgb, depth, alpha, xys, radii = res
+        rgb, depth, alpha, xys, radii = gsplat_ops.render_eval_fused(
+            params, vm, pm @ vm, c2w.detach().to("cpu", torch.float32)[:3, 3].tolist(), fx, fy, cx, cy, H, W,
+            sh_degree_active, background, defer_check=bool(state is not None and state.get("defer_check")))
         if state is not None:
             state["xys"], state["radii"] = xys, radii
         return {"rgb": rgb, "depth": depth, "accumulation": alpha}
@@ -136,7 +134,8 @@ class GaussCtrlModel(SplatfactoModel):
             camera.rescale_output_resolution(camera_downscale)
         sh_degree = getattr(self.config, "sh_degree", 3)
         n = min(self.step // getattr(self.config, "sh_degree_interval", 1000), sh_degree) if sh_degree > 0 else -1
-        state: dict = {}
+        # sync-free eval renders: the caller promises to call gsplat_ops.check_deferred_overflow() (render_reverse does)
+        state: dict = {"defer_check": bool(getattr(self, "defer_isect_check", False))}
         out = render_gaussians(params, camera.camera_to_worlds[0], *intr, H, W, n, background, training=self.training,
                                state=state)
         self.xys, self.radii = state.get("xys"), state.get("radii")
@@ -177,6 +176,8 @@ class GaussCtrlModel(SplatfactoModel):
         assert camera is not None, "must provide camera to gaussian model"
         self.set_crop(obb_box)
         self.training = False
-        outs = self.get_outputs(camera.to(self.device))
+        # the reference moves the camera to the device first (gc_model.py:219); the kernels here take the pose and the
+        # intrinsics as launch arguments, so a host-resident camera is read without a device synchronisation
+        outs = self.get_outputs(camera)
         self.training = True
         return outs  # type: ignore

@@ -61,32 +61,108 @@ def _spherical_harmonics_fwd(degrees_to_use: int, viewdirs, coeffs):
     return colors
 
 
+class _BinBuffers:
+    """Per-(device, N, tile grid) buffers of the binning, sized for an intersection CAPACITY instead of the exact count so
+    that nothing has to be read back before the kernels are enqueued.  The capacity is sticky and grows on overflow."""
+    cache: dict = {}
+
+    def __init__(self, N: int, tbx: int, tby: int, dev, cap: int):
+        self.N, self.tbx, self.tby, self.cap = N, tbx, tby, cap
+        self.gids = torch.empty((cap,), dtype=torch.int32, device=dev)
+        self.bins = torch.empty((tbx * tby, 2), dtype=torch.int32, device=dev)
+        self.count = torch.zeros((2,), dtype=torch.int32, device=dev)
+        nb = lib.gcb_bin_gaussians_workspace_bytes(N, cap, tbx, tby)
+        self.ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+
+    @classmethod
+    def get(cls, N: int, tbx: int, tby: int, dev, min_cap: int = 0) -> "_BinBuffers":
+        key = (str(dev), N, tbx, tby, torch.cuda.current_stream().cuda_stream)
+        buf = cls.cache.get(key)
+        if buf is None or buf.cap < min_cap:
+            cap = max(min_cap, 1 << 16, min(8 * N, (1 << 30) - 1)) if buf is None else max(min_cap, 2 * buf.cap)
+            cap = min(cap, (1 << 30) - 1)
+            buf = cls(N, tbx, tby, dev, cap)
+            if len(cls.cache) > 8:
+                cls.cache.clear()
+            cls.cache[key] = buf
+        return buf
+
+
+PENDING_OVERFLOW: list = []   # device flags of deferred (sync-free) binnings, see check_deferred_overflow()
+
+
+def _bin_launch(xys, depths, radii, num_tiles_hit, tbx: int, tby: int, buf: _BinBuffers, keys=None) -> None:
+    check(lib.gcb_bin_gaussians(_p(xys), _p(depths), _p(radii), _p(num_tiles_hit), depths.shape[0], tbx, tby, buf.cap,
+                                _p(buf.gids), _p(buf.bins), _p(buf.count), _p(keys), _p(buf.ws), buf.ws.numel(),
+                                _stream()))
+    ops.LAUNCHES[0] += 11
+
+
 def bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds, want_keys: bool = False):
-    """Depth-order the Gaussians, emit tile intersections, group by tile.
-    -> (gaussian_ids [M] i32, tile_bins [T,2] i32, isect_keys [M] i64 or None, M)."""
+    """Depth-order the Gaussians, emit tile intersections, group by tile (gcb_bin_gaussians).
+    -> (gaussian_ids [M] i32, tile_bins [T,2] i32, isect_keys [M] i64 or None, M).
+    This seam-level helper returns exactly-sized tensors, so it reads M back ONCE, after everything is enqueued (gsplat's
+    rasterize_gaussians has the same read in the middle of its pipeline); the eval render path does not read it at all."""
+    xys, depths = _f32(xys), _f32(depths)
     N, dev = depths.shape[0], depths.device
     tbx, tby = int(tile_bounds[0]), int(tile_bounds[1])
-    sorted_ids = torch.empty((N,), dtype=torch.int32, device=dev)
-    cum = torch.empty((N,), dtype=torch.int32, device=dev)
-    nb = lib.gcb_depth_order_workspace_bytes(N)
-    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-    check(lib.gcb_depth_order(_p(depths), _p(num_tiles_hit), N, _p(sorted_ids), _p(cum), _p(ws), nb, _stream()))
-    ops.LAUNCHES[0] += 16
-    M = int(cum[-1].item())  # the one host sync gsplat's rasterize_gaussians also has
+    buf = _BinBuffers.get(N, tbx, tby, dev)
+    while True:
+        keys = torch.empty((buf.cap,), dtype=torch.int64, device=dev) if want_keys else None
+        _bin_launch(xys, depths, radii, num_tiles_hit, tbx, tby, buf, keys)
+        M, overflow = (int(v) for v in buf.count.tolist())
+        if not overflow:
+            break
+        buf = _BinBuffers.get(N, tbx, tby, dev, min_cap=M)   # truncated: redo with room for all M intersections
     LAST_M[0] = M
-    gids = torch.empty((max(M, 1),), dtype=torch.int32, device=dev)
-    bins = torch.empty((tbx * tby, 2), dtype=torch.int32, device=dev)
-    keys = torch.empty((max(M, 1),), dtype=torch.int64, device=dev) if want_keys else None
-    nb2 = lib.gcb_bin_tiles_workspace_bytes(N, M, tbx, tby)
-    ws2 = torch.empty(max(nb2, 16), dtype=torch.uint8, device=dev)
-    check(lib.gcb_bin_tiles(_p(xys), _p(depths), _p(radii), _p(sorted_ids), _p(cum), N, M, tbx, tby, _p(gids), _p(bins),
-                            _p(keys), _p(ws2), ws2.numel(), _stream()))
-    ops.LAUNCHES[0] += 6
-    return gids[:M], bins, (keys[:M] if keys is not None else None), M
+    return buf.gids[:M].clone(), buf.bins.clone(), (keys[:M] if keys is not None else None), M
 
 
-def rasterize_sorted(xys, conics, colors, opacity, gids, bins, img_height, img_width, background):
-    """-> (img [H,W,C], final_T [H,W], final_idx [H,W])"""
+def check_deferred_overflow() -> None:
+    """One synchronisation for ALL sync-free renders since the last call: raises if any of them overflowed its
+    intersection capacity (the images it produced are truncated and must be re-rendered; the capacity has been grown)."""
+    global PENDING_OVERFLOW
+    pend, PENDING_OVERFLOW = PENDING_OVERFLOW, []
+    if not pend:
+        return
+    counts = torch.stack([c for c, _ in pend]).cpu()
+    LAST_M[0] = int(counts[-1, 0])
+    bad = [(int(counts[i, 0]), pend[i][1]) for i in range(len(pend)) if int(counts[i, 1])]
+    if bad:
+        for m, key in bad:
+            _BinBuffers.get(*key, min_cap=m)
+        raise IsectOverflow(f"{len(bad)} render(s) exceeded the intersection capacity (largest M = {max(m for m, _ in bad)});"
+                            f" capacity grown - render again")
+
+
+class IsectOverflow(RuntimeError):
+    pass
+
+
+def render_views_multistream(render_one, items, streams):
+    """Run `render_one(item)` for every item, item i on stream i % len(streams), and join them on the current stream.
+    The binning kernels of one view are latency-bound (look-back chains, ~250-2000 blocks of dependent work) and leave
+    most of the GPU idle; a second and third view on other streams fill it.  Every stream has its own binning workspace
+    (_BinBuffers is keyed by stream); outputs are handed to the current stream with `record_stream`."""
+    cur = torch.cuda.current_stream()
+    for s in streams:
+        s.wait_stream(cur)
+    outs = []
+    for i, item in enumerate(items):
+        s = streams[i % len(streams)]
+        with torch.cuda.stream(s):
+            out = render_one(item)
+        for v in (out.values() if isinstance(out, dict) else out):
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                v.record_stream(cur)
+        outs.append(out)
+    for s in streams:
+        cur.wait_stream(s)
+    return outs
+
+
+def rasterize_sorted(xys, conics, colors, opacity, gids, bins, img_height, img_width, background, radii=None):
+    """-> (img [H,W,C], final_T [H,W], final_idx [H,W]).  `radii` (optional) only enables per-warp culling."""
     colors = _f32(colors)
     C = colors.shape[1]
     dev = colors.device
@@ -96,7 +172,7 @@ def rasterize_sorted(xys, conics, colors, opacity, gids, bins, img_height, img_w
     fidx = torch.empty((H, W), dtype=torch.int32, device=dev)
     bg = (ctypes.c_float * C)(*[float(v) for v in background.detach().cpu().reshape(-1).tolist()])
     check(lib.gcb_rasterize_fwd(_p(_f32(xys)), _p(_f32(conics)), _p(colors), _p(_f32(opacity).reshape(-1)), _p(gids),
-                                _p(bins), H, W, C, bg, _p(out), _p(fT), _p(fidx), _stream()))
+                                _p(bins), _p(radii), H, W, C, bg, _p(out), _p(fT), _p(fidx), _stream()))
     ops.LAUNCHES[0] += 1
     return out, fT, fidx
 
@@ -154,7 +230,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         H, W = int(img_height), int(img_width)
         tile_bounds = ((W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK, 1)
         gids, bins, _, M = bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds)
-        img, fT, fidx = rasterize_sorted(xys, conics, colors, opacity, gids, bins, H, W, background)
+        img, fT, fidx = rasterize_sorted(xys, conics, colors, opacity, gids, bins, H, W, background, radii=radii)
         ctx.save_for_backward(_f32(xys), _f32(conics), _f32(colors), _f32(opacity).reshape(-1), gids, bins, fT, fidx,
                               background.detach().to("cpu", torch.float32))
         ctx.size = (H, W)
@@ -206,10 +282,12 @@ def rasterize_gaussians(xys, depths, radii, conics, num_tiles_hit, colors, opaci
 
 
 def render_eval_fused(params, viewmat, projmat, cam_origin, fx, fy, cx, cy, img_height, img_width, sh_degree,
-                      background):
+                      background, defer_check: bool = False):
     """Eval-mode get_outputs in 3 stages on raw splatfacto parameters: fused project+SH+activations (one pass over the
-    236 B/Gaussian record), binning, fused rgb+depth composite + epilogue.
-    -> (rgb [H,W,3], depth [H,W,1], alpha [H,W,1], xys, radii) or None when nothing is visible."""
+    236 B/Gaussian record), binning (11 launches, intersection count stays on the device), fused rgb+depth composite with
+    the clamp / depth-normalise epilogue.  No host synchronisation in between; `defer_check=True` also defers the
+    capacity-overflow check to `check_deferred_overflow()` so that consecutive views pipeline on the GPU.
+    -> (rgb [H,W,3], depth [H,W,1], alpha [H,W,1], xys, radii)."""
     means = _f32(params["means"])
     N, dev = means.shape[0], means.device
     H, W = int(img_height), int(img_width)
@@ -229,16 +307,20 @@ def render_eval_fused(params, viewmat, projmat, cam_origin, fx, fy, cx, cy, img_
                                        float(fx), float(fy), float(cx), float(cy), H, W, tbx, tby, int(sh_degree), N,
                                        _p(xys), _p(depths), _p(radii), _p(conics), _p(nth), _p(rgbd), _p(opac), _stream()))
     ops.LAUNCHES[0] += 1
-    gids, bins, _, M = bin_and_sort(xys, depths, radii, nth, (tbx, tby, 1))
-    if M < 1:
-        return None
-    bg4 = torch.cat([background.detach().to("cpu", torch.float32).reshape(3), torch.zeros(1)])
-    img4, fT, _ = rasterize_sorted(xys, conics, rgbd, opac, gids, bins, H, W, bg4)
+    buf = _BinBuffers.get(N, tbx, tby, dev)
+    _bin_launch(xys, depths, radii, nth, tbx, tby, buf)
     rgb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
     depth = torch.empty((H, W, 1), dtype=torch.float32, device=dev)
     alpha = torch.empty((H, W, 1), dtype=torch.float32, device=dev)
-    check(lib.gcb_raster_finalize(_p(img4), _p(fT), _p(rgb), _p(depth), _p(alpha), H * W, _stream()))
+    bg3 = background.detach().to(dev, torch.float32).reshape(3).contiguous()   # stays on the device: no sync
+    check(lib.gcb_rasterize_rgbd_fwd(_p(xys), _p(conics), _p(rgbd), _p(opac), _p(buf.gids), _p(buf.bins), _p(radii), H, W,
+                                     _p(bg3), _p(rgb), _p(depth), _p(alpha), _stream()))
     ops.LAUNCHES[0] += 1
+    # M == 0 needs no special case: every tile run is empty, so rgb = background, depth = 1000, alpha = 0 - what the
+    # reference returns for `radii.sum() == 0` plus the two keys it omits there (gc_model.py:155-156)
+    PENDING_OVERFLOW.append((buf.count.clone(), (N, tbx, tby, dev)))
+    if not defer_check:
+        check_deferred_overflow()
     return rgb, depth, alpha, xys, radii
 
 
@@ -251,11 +333,11 @@ def rasterize_rgbd(xys, depths, radii, conics, num_tiles_hit, rgbs, opacity, img
     tile_bounds = ((W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK, 1)
     gids, bins, _, M = bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds)
     col4 = torch.cat([_f32(rgbs), _f32(depths)[:, None]], dim=1).contiguous()
-    bg4 = torch.cat([background.detach().to(dev, torch.float32).reshape(3), torch.zeros(1, device=dev)])
-    img4, fT, _ = rasterize_sorted(xys, conics, col4, opacity, gids, bins, H, W, bg4)
     rgb = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
     depth = torch.empty((H, W, 1), dtype=torch.float32, device=dev)
     alpha = torch.empty((H, W, 1), dtype=torch.float32, device=dev)
-    check(lib.gcb_raster_finalize(_p(img4), _p(fT), _p(rgb), _p(depth), _p(alpha), H * W, _stream()))
+    bg3 = background.detach().to(dev, torch.float32).reshape(3).contiguous()
+    check(lib.gcb_rasterize_rgbd_fwd(_p(_f32(xys)), _p(_f32(conics)), _p(col4), _p(_f32(opacity).reshape(-1)), _p(gids),
+                                     _p(bins), _p(radii), H, W, _p(bg3), _p(rgb), _p(depth), _p(alpha), _stream()))
     ops.LAUNCHES[0] += 1
     return rgb, depth, alpha

@@ -170,29 +170,38 @@ int gcb_project_sh_fused_fwd(const float* means3d, const float* log_scales, cons
 size_t gcb_scan_workspace_bytes(int N);
 int gcb_cumsum_i32(const int32_t* in, int32_t* out, int N, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Tile binning (gsplat map_gaussian_to_intersects + torch.sort + get_tile_bin_edges, inside each
- * rasterize_gaussians call, gc_model.py:174-186 and :191-202), re-designed: order the N Gaussians by depth
- * once (stable, ties by id), emit their tile intersections in that order, one stable radix pass by tile id.
- * The result equals a STABLE sort of (tile_id << 32 | depth bits) keys.
- *   step 1  gcb_depth_order: sorted_ids [N] and cum_sorted [N] = inclusive cumsum of num_tiles_hit in that order;
- *           the caller reads M = cum_sorted[N-1] back (the one host sync gsplat also has).
- *   step 2  gcb_bin_tiles:   gaussian_ids [M] (sorted), tile_bins [tiles,2] (start,end; 0,0 for empty tiles),
- *           optional isect_keys [M] i64 (NULL to skip; needs depths). */
-size_t gcb_depth_order_workspace_bytes(int N);
-int gcb_depth_order(const float* depths, const int32_t* num_tiles_hit, int N, int32_t* sorted_ids, int32_t* cum_sorted,
-                    void* workspace, size_t workspace_bytes, void* stream);
-size_t gcb_bin_tiles_workspace_bytes(int N, long long M, int tile_bx, int tile_by);
-int gcb_bin_tiles(const float* xys, const float* depths, const int32_t* radii, const int32_t* sorted_ids,
-                  const int32_t* cum_sorted, int N, long long M, int tile_bx, int tile_by, int32_t* gaussian_ids,
-                  int32_t* tile_bins, int64_t* isect_keys, void* workspace, size_t workspace_bytes, void* stream);
+/* Tile binning (gsplat cumsum + map_gaussian_to_intersects + torch.sort + get_tile_bin_edges, inside each
+ * rasterize_gaussians call, gc_model.py:174-186 and :191-202), re-designed and WITHOUT the host round trip gsplat has
+ * for the intersection count: order the N Gaussians by depth once (stable 8-bit radix passes, ties by id), emit their
+ * tile intersections in that order, one stable radix pass by tile id (two above 2048 tiles).  The result equals a STABLE
+ * sort of (tile_id << 32 | depth bits) keys.
+ *   isect_capacity  room (in intersections) of gaussian_ids / isect_keys and of the workspace: the caller sizes it;
+ *   gaussian_ids    [isect_capacity] i32: the first M entries are the sorted Gaussian ids;
+ *   tile_bins       [tiles,2] i32 (start, end) of every tile's run (start == end for an empty tile);
+ *   isect_count     device int32[2]: [0] = M (the true count), [1] = 1 when M > isect_capacity - nothing is written
+ *                   out of bounds then, the result is truncated and the caller re-runs with a larger capacity;
+ *   isect_keys      optional [isect_capacity] i64 = the sorted 64-bit keys (NULL to skip).
+ * Every kernel reads M from `isect_count` on the device; the call never synchronises. */
+size_t gcb_bin_gaussians_workspace_bytes(int N, long long isect_capacity, int tile_bx, int tile_by);
+int gcb_bin_gaussians(const float* xys, const float* depths, const int32_t* radii, const int32_t* num_tiles_hit, int N,
+                      int tile_bx, int tile_by, long long isect_capacity, int32_t* gaussian_ids, int32_t* tile_bins,
+                      int32_t* isect_count, int64_t* isect_keys, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-tile front-to-back alpha compositing (gsplat rasterize_forward).  colors [N,C] with C in {1,3,4};
  * background host float[C].  Outputs: out_img [H,W,C], final_T [H,W], final_idx [H,W] i32.
  * C=4 with colors = (r,g,b,depth) is the fused rgb+depth pass that replaces the reference's TWO rasterize calls
- * (gc_model.py:174-202). */
+ * (gc_model.py:174-202).  radii [N] i32 (project_gaussians' output, may be NULL): lets every warp skip Gaussians
+ * that cannot reach alpha >= 1/255 anywhere in its 8x4 pixel sub-block; the image is bit-identical with or without it. */
 int gcb_rasterize_fwd(const float* xys, const float* conics, const float* colors, const float* opacities,
-                      const int32_t* gaussian_ids, const int32_t* tile_bins, int img_h, int img_w, int C,
-                      const float* h_background, float* out_img, float* final_T, int32_t* final_idx, void* stream);
+                      const int32_t* gaussian_ids, const int32_t* tile_bins, const int32_t* radii, int img_h, int img_w,
+                      int C, const float* h_background, float* out_img, float* final_T, int32_t* final_idx, void* stream);
+/* The eval branch of GaussCtrlModel.get_outputs in ONE composite (gc_model.py:174-204 runs two rasterize calls and
+ * three elementwise passes): rgbd [N,4] = (r,g,b,depth) per Gaussian, d_background3 DEVICE float[3] (no host read);
+ * out_rgb [H,W,3] = min(rgb + T*bg, 1), out_alpha [H,W] = 1 - T, out_depth [H,W] = depth / alpha (1000 where alpha == 0). */
+int gcb_rasterize_rgbd_fwd(const float* xys, const float* conics, const float* rgbd, const float* opacities,
+                           const int32_t* gaussian_ids, const int32_t* tile_bins, const int32_t* radii, int img_h,
+                           int img_w, const float* d_background3, float* out_rgb, float* out_depth, float* out_alpha,
+                           void* stream);
 
 /* ---- backward (the 3DGS fine-tune step after the edit: gc_trainer.py:257-301 -> loss.backward() through gsplat's
  *      autograd Functions).  Exact derivatives of the forward kernels above. ---- */

@@ -35,7 +35,8 @@ def test_argument_validation_without_gpu():
     assert lib.gcb_geglu_pack_rows(512, perm) == 0
     p = list(perm)
     assert sorted(p) == list(range(512)) and p[:3] == [0, 1, 2] and p[128] == 256  # value|gate halves per 256 tile
-    assert lib.gcb_scan_workspace_bytes(1 << 20) > 0 and lib.gcb_depth_order_workspace_bytes(1000) > 4000
+    assert lib.gcb_scan_workspace_bytes(1 << 20) > 0 and lib.gcb_bin_gaussians_workspace_bytes(1000, 65536, 32, 32) > 4000
+    assert lib.gcb_bin_gaussians_workspace_bytes(0, 65536, 32, 32) == 0
 
 
 def test_no_cpu_fallback():

@@ -98,6 +98,76 @@ def test_bin_and_sort_exact(N, H, W):
     assert np.array_equal(b[~nonempty, 1] - b[~nonempty, 0], np.zeros((~nonempty).sum(), dtype=np.int32))
 
 
+def test_binning_capacity_overflow_is_flagged_and_recovered():
+    """gcb_bin_gaussians never reads M on the host: with too small a capacity it truncates (no out-of-bounds write), raises
+    the device flag and reports the true M; bin_and_sort then re-runs with room for M.  Also: > 2048 tiles (two tile
+    passes) on a 1024x768 image, and the prefix-sum entry point."""
+    import ctypes
+    from oracle import gsplat_ref as gr
+    from gaussctrl_b200 import gsplat_ops as go
+    from gaussctrl_b200._lib import check, lib
+    N, H, W = 6000, 768, 1024
+    P, c2w, (fx, fy, cx, cy), vm, pm, tb, scales, quats = _project_inputs(N, H, W, seed=4)
+    assert tb[0] * tb[1] == 3072
+    xys, depths, radii, conics, nth, _ = gr.project_gaussians(P["means"], scales, 1, quats, vm[:3], pm @ vm, fx, fy, cx,
+                                                              cy, H, W, tb)
+    keys_w, gids_w, bins_w = gr.bin_and_sort_vectorized(xys, depths, radii, nth, tb)
+    M_true = len(gids_w)
+    assert M_true > 65536            # larger than the initial capacity of a small scene -> the retry path runs
+    go._BinBuffers.cache.clear()
+    gids, bins, keys, M = go.bin_and_sort(xys.cuda(), depths.cuda(), radii.cuda(), nth.cuda(), tb, want_keys=True)
+    assert M == M_true
+    assert np.array_equal(gids.cpu().numpy(), gids_w) and np.array_equal(keys.cpu().numpy(), keys_w)
+    assert np.array_equal(bins.cpu().numpy(), bins_w)
+    # explicit truncated call
+    cap = 4096
+    dev = "cuda"
+    g = torch.full((cap + 64,), -7, dtype=torch.int32, device=dev)
+    b = torch.empty((tb[0] * tb[1], 2), dtype=torch.int32, device=dev)
+    cnt = torch.zeros(2, dtype=torch.int32, device=dev)
+    nb = lib.gcb_bin_gaussians_workspace_bytes(N, cap, tb[0], tb[1])
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    args = [t.cuda().contiguous() for t in (xys, depths, radii, nth)]
+    check(lib.gcb_bin_gaussians(*[a.data_ptr() for a in args], N, tb[0], tb[1], cap, g.data_ptr(), b.data_ptr(),
+                                cnt.data_ptr(), None, ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert cnt.tolist() == [M_true, 1]
+    assert (g[cap:] == -7).all()                                   # nothing written past the capacity
+    assert int((b[:, 1] - b[:, 0]).sum().item()) == cap            # the bins describe exactly the truncated set
+    # gcb_cumsum_i32 (single-pass scan) against torch
+    x = torch.randint(0, 50, (100_003,), dtype=torch.int32, device=dev)
+    y = torch.empty_like(x)
+    nbs = lib.gcb_scan_workspace_bytes(x.numel())
+    wss = torch.empty(nbs, dtype=torch.uint8, device=dev)
+    check(lib.gcb_cumsum_i32(x.data_ptr(), y.data_ptr(), x.numel(), wss.data_ptr(), nbs,
+                             torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(y, torch.cumsum(x, 0).to(torch.int32))
+
+
+def test_deferred_overflow_check_and_empty_view():
+    """Sync-free eval renders: results identical to the checked path; a camera that sees nothing gives the background,
+    depth 1000 and zero coverage (M == 0 needs no special case)."""
+    from gaussctrl_b200 import gsplat_ops as go
+    from gaussctrl_b200.gc_model import render_gaussians
+    N, H, W = 4000, 96, 80
+    P = {k: v.cuda() for k, v in _scene(N, seed=17).items()}
+    c2w, fx, fy, cx, cy = _camera(H, W)
+    bg = torch.tensor([0.2, 0.4, 0.1]).cuda()
+    with torch.no_grad():
+        a = render_gaussians(P, c2w, fx, fy, cx, cy, H, W, 3, bg)
+        b = render_gaussians(P, c2w, fx, fy, cx, cy, H, W, 3, bg, state={"defer_check": True})
+        assert len(go.PENDING_OVERFLOW) == 1
+        go.check_deferred_overflow()
+        assert go.PENDING_OVERFLOW == [] and go.LAST_M[0] > 0
+        for k in ("rgb", "depth", "accumulation"):
+            assert torch.equal(a[k], b[k])
+        away = c2w.clone()
+        away[:3, 2] = -away[:3, 2]          # look the other way
+        away[:3, 0] = -away[:3, 0]
+        e = render_gaussians(P, away, fx, fy, cx, cy, H, W, 3, bg)
+    assert torch.equal(e["rgb"], bg.expand(H, W, 3)) and (e["depth"] == 1000).all() and (e["accumulation"] == 0).all()
+
+
 @pytest.mark.parametrize("C", [1, 3, 4])
 def test_rasterize_forward(C):
     from oracle import gsplat_ref as gr
@@ -121,6 +191,10 @@ def test_rasterize_forward(C):
     # last-contributor index: identical except where a threshold decision sits within rounding of its boundary
     mism = (fidx.cpu().numpy() != fidx_w).mean()
     assert mism < 2e-3, mism
+    # per-warp culling from the projected radii never changes a bit of the result
+    img_c, fT_c, fidx_c = go.rasterize_sorted(xys.cuda(), conics.cuda(), colors.cuda(), opac.cuda(), gids, bins, H, W, bg,
+                                              radii=radii.cuda())
+    assert torch.equal(img_c, img) and torch.equal(fT_c, fT) and torch.equal(fidx_c, fidx)
 
 
 def test_get_outputs_fused_rgbd():

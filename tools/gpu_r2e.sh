@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests/test_raster_gpu.py tests/test_z_fullsize_properties_gpu.py tests/test_z_fullsize_elementwise_gpu.py tests/test_pipeline_gpu.py tests/test_finetune_gpu.py -x -q 2>&1 | tail -15 > gpurun_out/r2e_tests.log
+cat gpurun_out/r2e_tests.log
+python tools/time_raster.py 1000000 40 > gpurun_out/r2e_raster_time.json 2>gpurun_out/r2e_raster_time.err
+cat gpurun_out/r2e_raster_time.json; tail -3 gpurun_out/r2e_raster_time.err
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -c 45 --csv --log-file gpurun_out/r2e_raster_launches_warm.csv python tools/time_raster.py 1000000 2 > gpurun_out/r2e_ncu.log 2>&1
+tail -2 gpurun_out/r2e_ncu.log
