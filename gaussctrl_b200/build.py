@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libgaussctrl_b200.so")
 SOURCES = ["api.cu", "gemm_tc.cu", "gemm_simt.cu", "attn_mma.cu", "attn_tc.cu", "norm.cu", "elementwise.cu", "raster.cu", "raster_bin.cu", "raster_bwd.cu",
-           "finetune.cu", "clip.cu"]
+           "finetune.cu", "clip.cu", "peer.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -102,7 +102,7 @@ class _ShardedRefStep:
         self.cond_all = torch.zeros((R, hw, hw, den.ch[0]), dtype=torch.float16, device=dev)
         self.t = torch.zeros((self.per,), dtype=torch.float32, device=dev)
         self.coef = torch.zeros((4,), dtype=torch.float32, device=dev)
-        self.eps_all = torch.zeros((world * self.per, hw, hw, 4), dtype=torch.float16, device=dev)
+        self.gather = gather
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches = 0
@@ -111,13 +111,14 @@ class _ShardedRefStep:
         self.cond_all.copy_(cond_emb)
 
     def _body(self) -> None:
-        import torch.distributed as dist
+        # the peers may still be reading last step's gathered K/V in their view batches: barrier before re-writing it
+        self.gather.begin_pass()
         xin = self.x[self.lat_of_row]
         cond = self.cond_all[self.lat_of_row]
         eps = self.den.eps(xin, self.t, cond, self.plan)
-        dist.all_gather_into_tensor(self.eps_all, eps.contiguous())
+        eps_all = self.gather("eps", eps.contiguous())          # [world*per, hw, hw, 4]: 32 KB per row
         R = self.R
-        ops.cfg_ddim_step(self.eps_all[:R], self.eps_all[R:2 * R], self.x, self.guidance, self.coef, out=self.x)
+        ops.cfg_ddim_step(eps_all[:R], eps_all[R:2 * R], self.x, self.guidance, self.coef, out=self.x)
 
     run = _GraphedStep.run
 
@@ -200,9 +201,9 @@ class EditEngine:
         K/V; (2) the remaining views are denoised in batches of `view_batch`, reading that K/V.
         Reference views' own edited latents are rows of pass (1) (SURVEY §8a gotcha 6).
         `view_ids`: the subset of views this rank edits (multi-GPU sharding); default all.
-        `dist_ctx` = {"world", "rank", "gather": parallel.KVAllGather, "graph_refs": bool (default False: capturing the
-        NCCL all-gathers of the sharded reference pass in a CUDA graph deadlocked on the 2-GPU box, so that pass runs
-        eagerly; the view batches - 90 % of the work - are still graph replays)}: the reference pass is
+        `dist_ctx` = {"world", "rank", "gather": parallel.PeerKVAllGather (our NVLink peer-memory kernels, captured in the
+        reference pass's CUDA graph) or parallel.KVAllGather (NCCL, eager), "graph_refs": optional override}: the
+        reference pass is
         sharded over the ranks' CFG rows with a per-layer K/V all-gather; result rows of views this rank does not own
         stay zero (parallel.gather_view_results assembles them)."""
         assert guidance > 1.0
@@ -223,8 +224,11 @@ class EditEngine:
         key = ("refs_once", R, bsz, hw, float(guidance), tuple(ref_frames), world)
         if key not in self._steps:
             if world > 1:
+                # our peer-memory exchange is plain kernels and is captured with the rest of the pass; the NCCL
+                # all-gather stays eager (capturing it deadlocked on the 2-GPU box in round 1)
+                capturable = bool(getattr(dist_ctx["gather"], "graph_capturable", False))
                 rs = _ShardedRefStep(self.den, R, guidance, hw, world, dist_ctx["rank"], dist_ctx["gather"], ref_frames,
-                                     self.use_graphs and dist_ctx.get("graph_refs", False))
+                                     self.use_graphs and dist_ctx.get("graph_refs", capturable))
                 self._steps[key] = [rs, rs.rec, None]
             else:
                 rec0: Dict[str, torch.Tensor] = {}
@@ -258,6 +262,8 @@ class EditEngine:
                 view_step.set_cond(conds[bi])
                 view_step.run(t, coefs)
                 x_views[bi].copy_(view_step.x)
+        if world > 1:
+            dist_ctx["gather"].check()   # one synchronisation per edit: did every wait of the K/V exchange complete?
         out = torch.zeros_like(x_all)
         for ri, v in enumerate(ref_indices):
             out[v].copy_(ref_step.x[ri])

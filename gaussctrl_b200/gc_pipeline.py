@@ -202,18 +202,7 @@ class GaussCtrlPipeline(VanillaPipeline):
         for attempt in range(2):
             # all of this rank's views are enqueued without a host synchronisation (the intersection counts stay on the
             # device); ONE check afterwards, and a second pass only if a view outgrew the intersection capacity
-            model.defer_isect_check = True
-            try:
-                if self.device_.type == "cuda" and self.raster_streams > 1:
-                    # the binning kernels of one view leave most of the GPU idle: views are spread over a few streams
-                    if getattr(self, "_raster_streams", None) is None:
-                        self._raster_streams = [torch.cuda.Stream(self.device_) for _ in range(self.raster_streams)]
-                    outs = gsplat_ops.render_views_multistream(
-                        lambda ci: model.get_outputs_for_camera(self._camera_at(ci)), mine, self._raster_streams)
-                else:
-                    outs = [model.get_outputs_for_camera(self._camera_at(ci)) for ci in mine]
-            finally:
-                model.defer_isect_check = False
+            outs = self.render_views(mine)
             rgbs = [o["rgb"].to(torch.float16) for o in outs]          # [H,W,3] 0..1   (:132)
             depths = [o["depth"].to(torch.float16) for o in outs]      # [H,W,1]        (:133)
             try:
@@ -259,6 +248,23 @@ class GaussCtrlPipeline(VanillaPipeline):
             self._store_view(cam_idx, rgb_h[j].clone(), depth_h[j].numpy().copy(), z_h[j:j + 1].numpy().copy(),
                              None if masks is None else masks[j])
 
+    def render_views(self, view_ids: Sequence[int]) -> List[Dict[str, torch.Tensor]]:
+        """Eval renders (`model.get_outputs_for_camera`) of the given views, enqueued without any host synchronisation
+        and spread over `raster_streams` CUDA streams (the binning kernels of one view leave most of the GPU idle).
+        The caller runs `gsplat_ops.check_deferred_overflow()` afterwards."""
+        from . import gsplat_ops
+        model = self.model
+        model.defer_isect_check = True
+        try:
+            if self.device_.type == "cuda" and self.raster_streams > 1:
+                if getattr(self, "_raster_streams", None) is None:
+                    self._raster_streams = [torch.cuda.Stream(self.device_) for _ in range(self.raster_streams)]
+                return gsplat_ops.render_views_multistream(
+                    lambda ci: model.get_outputs_for_camera(self._camera_at(ci)), list(view_ids), self._raster_streams)
+            return [model.get_outputs_for_camera(self._camera_at(ci)) for ci in view_ids]
+        finally:
+            model.defer_isect_check = False
+
     # batch sizes of stage A (B200 extension; results do not depend on them: batch-invariant kernels)
     raster_streams = 4   # concurrent eval renders (measured on B200, 1 M Gaussians: 0.51 -> 0.36 ms per view)
     stage_a_batch = 8    # views per VAE-encode launch set (512^2 x 128-channel activations: 67 MB per view and layer)
@@ -282,37 +288,68 @@ class GaussCtrlPipeline(VanillaPipeline):
         decoded by one rank, and the decoded images are all-gathered so EVERY rank's train_data is complete (the
         fine-tune that follows samples any view on any rank)."""
         td = self.datamanager.train_data
-        V = len(td)
         dev = self.device_
-        S, g = self.num_inference_steps, float(self.guidance_scale)
-        if g <= 1.0:
-            # diffusers does not double the batch for CFG then, and CrossViewAttnProcessor's `video_length = B // 2`
-            # (utils.py:94) silently mixes views: every shipped script uses g in {3, 5, 7.5} (SURVEY §8a gotcha 2)
-            raise ValueError(f"guidance_scale={g} <= 1: the cross-view attention layout needs classifier-free guidance")
-        world, rank = self._dist()
-        refs = list(self.ref_indices)
-        R = self.num_ref_views
-        reference_schedule = self.config.edit_schedule == "reference"
-        if world > 1 and reference_schedule:
-            raise ValueError("edit_schedule='reference' is the single-GPU literal schedule; multi-GPU runs use 'refs_once'")
-        from . import parallel as par
-        if world > 1:
-            view_ids = par.shard_views(V, world, rank, refs)
-            mine = sorted(view_ids + [refs[i] for i in par.ref_decode_owner(R, world, rank)])
-        else:
-            view_ids, mine = None, list(range(V))
-        need = list(range(V)) if world == 1 else sorted(set(mine) | set(refs))   # views this rank uploads
-        pos_of = {v: j for j, v in enumerate(need)}
+        plan = self.edit_plan(len(td))
+        need, mine = plan["need"], plan["mine"]
         z = _pinned(torch.from_numpy(np.concatenate([td[i]["z_0_image"] for i in need], axis=0)))
         dep = _pinned(torch.from_numpy(np.concatenate([td[i]["depth_image"] for i in need], axis=0)))
         z_dev = z.to(dev, non_blocking=True).to(torch.float16)
         dep_dev = dep.to(dev, non_blocking=True)
         self.h2d_bytes = z.numel() * 4 + dep.numel() * 4
+        masks = uned = None
+        if all("mask_image" in td[i] for i in mine):
+            masks = torch.from_numpy(np.stack([np.asarray(td[i]["mask_image"], dtype=np.float32) for i in mine])).to(dev)
+            uned = torch.stack([td[i]["unedited_image"] for i in mine]).to(dev, torch.float16)
+            self.h2d_bytes += masks.numel() * 4 + uned.numel() * 2
+        imgs, ids = self.edit_on_device(z_dev, dep_dev, plan, masks, uned)
+        host = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=imgs.is_cuda)
+        host.copy_(imgs, non_blocking=True)
+        if imgs.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        self.d2h_bytes = host.numel() * 4
+        for j, i in enumerate(ids):
+            # global_idx = image_idx (gc_pipeline.py:224,234); own storage per view: the datamanager deep-copies entries
+            td[int(td[i].get("image_idx", i))]["image"] = host[j].clone()
+
+    def edit_plan(self, V: int) -> dict:
+        """Who edits what: `mine` = views this rank decodes, `view_ids` = its non-reference views (None on one GPU),
+        `need` = views whose stage-A products it uploads (its own + the references), `pos_of` = view id -> row in `need`."""
+        world, rank = self._dist()
+        refs = list(self.ref_indices)
+        from . import parallel as par
+        if world > 1:
+            view_ids = par.shard_views(V, world, rank, refs)
+            mine = sorted(view_ids + [refs[i] for i in par.ref_decode_owner(self.num_ref_views, world, rank)])
+            need = sorted(set(mine) | set(refs))
+        else:
+            view_ids, mine, need = None, list(range(V)), list(range(V))
+        return {"V": V, "world": world, "rank": rank, "view_ids": view_ids, "mine": mine, "need": need,
+                "pos_of": {v: j for j, v in enumerate(need)}}
+
+    @torch.no_grad()
+    def edit_on_device(self, z_dev: torch.Tensor, dep_dev: torch.Tensor, plan: dict, masks: Optional[torch.Tensor] = None,
+                       uned: Optional[torch.Tensor] = None):
+        """The device part of edit_images: z_dev [len(need),4,h,w] fp16 latents and dep_dev [len(need),H,W] fp32 depth of
+        the views in `plan["need"]` -> (edited images [n,H,W,3] fp32 on the device, their view ids).  On several GPUs the
+        images of all ranks are all-gathered, so n = V on every rank."""
+        S, g = self.num_inference_steps, float(self.guidance_scale)
+        if g <= 1.0:
+            # diffusers does not double the batch for CFG then, and CrossViewAttnProcessor's `video_length = B // 2`
+            # (utils.py:94) silently mixes views: every shipped script uses g in {3, 5, 7.5} (SURVEY §8a gotcha 2)
+            raise ValueError(f"guidance_scale={g} <= 1: the cross-view attention layout needs classifier-free guidance")
+        V, world, rank = plan["V"], plan["world"], plan["rank"]
+        view_ids, mine, pos_of = plan["view_ids"], plan["mine"], plan["pos_of"]
+        refs = list(self.ref_indices)
+        R = self.num_ref_views
+        from . import parallel as par
         # depth2disparity (numpy fp32, then .to(float16): gc_pipeline.py:182-186, 198-200), per view
         disparity = ops.nhwc_to_nchw(ops.depth_to_disparity(dep_dev.contiguous(), False))
         emb = self.prompt_encoder([self.negative_prompts, self.positive_prompt])
         neg, pos = emb[0:1], emb[1:2]
-        if reference_schedule:
+        if self.config.edit_schedule == "reference":
+            if world > 1:
+                raise ValueError("edit_schedule='reference' is the single-GPU literal schedule; multi-GPU runs use "
+                                 "'refs_once'")
             outs = []
             for i in range(0, V, self.chunk_size):
                 sel = refs + list(range(i, min(V, i + self.chunk_size)))
@@ -323,30 +360,18 @@ class GaussCtrlPipeline(VanillaPipeline):
             dist_ctx = None
             if world > 1:
                 if getattr(self, "_kv_gather", None) is None:
-                    self._kv_gather = par.make_kv_gather(dev)
+                    self._kv_gather = par.make_kv_gather(self.device_)
                 dist_ctx = {"world": world, "rank": rank, "gather": self._kv_gather}
             vb = max(1, getattr(self, "view_batch", getattr(self.config, "view_batch", self.chunk_size)))
             lat = self.engine.edit_refs_once(z_dev, disparity, [pos_of[r] for r in refs], pos, neg, S, g, view_batch=vb,
                                              view_ids=None if view_ids is None else [pos_of[v] for v in view_ids],
                                              dist_ctx=dist_ctx, ref_frames=crossview_ref_frames(R))
-        masks = uned = None
-        if all("mask_image" in td[i] for i in mine):
-            masks = torch.from_numpy(np.stack([np.asarray(td[i]["mask_image"], dtype=np.float32) for i in mine])).to(dev)
-            uned = torch.stack([td[i]["unedited_image"] for i in mine]).to(dev, torch.float16)
-            self.h2d_bytes += masks.numel() * 4 + uned.numel() * 2
         imgs = self.vae.decode_latents(lat[[pos_of[i] for i in mine]], masks, uned)         # [n,H,W,3] fp32
         ids = mine
         if world > 1:
             imgs = par.gather_view_results(imgs, mine, V, world)    # every rank ends up with all V edited images
             ids = list(range(V))
-        host = torch.empty(imgs.shape, dtype=torch.float32, pin_memory=imgs.is_cuda)
-        host.copy_(imgs, non_blocking=True)
-        if imgs.is_cuda:
-            torch.cuda.current_stream().synchronize()
-        self.d2h_bytes = host.numel() * 4
-        for j, i in enumerate(ids):
-            # global_idx = image_idx (gc_pipeline.py:224,234); own storage per view: the datamanager deep-copies entries
-            td[int(td[i].get("image_idx", i))]["image"] = host[j].clone()
+        return imgs, ids
 
     # ------------------------------------------------------------------------------------------ helpers (same names)
     @torch.no_grad()

@@ -16,6 +16,7 @@ from ._lib import (GCB_ACT_GEGLU, GCB_ACT_NONE, GCB_ACT_SILU, GCB_ATTN_AUTO, GCB
                    lib)
 
 LAUNCHES = [0]  # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
+ATTN_EVENTS = None  # set to a list: attention() appends (B, Nq, Nk, heads, d, n_active_sources, start_event, end_event)
 GEMM_LOG = None  # set to a list to record (B, H, W, Cin, Cout, ksize, act, has_bias, has_rowvec, has_residual) per conv2d call
 
 _GEMM_IMPL = [GCB_GEMM_TCGEN05]
@@ -156,10 +157,17 @@ def attention(q: torch.Tensor, q_off: int, ld_q: int, kv: torch.Tensor, k_off: i
     assert src_index.dtype == torch.int32 and src_index.numel() == B * n_src and src_index.is_cuda
     w = (ctypes.c_float * n_src)(*[float(v) for v in weights])
     sc = d ** -0.5 if scale is None else scale
+    ev = None
+    if ATTN_EVENTS is not None:   # in-situ timing (bench.py roofline): events on the launching stream around this kernel
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     check(lib.gcb_attn_multi_fwd(_p(q, q_off), ld_q, _p(kv, k_off), _p(kv, v_off), ld_kv, _p(kv2, k2_off),
                                  _p(kv2, v2_off), ld_kv2, _p(out), heads * d, B, Nq, Nk, heads, d,
                                  d if v_head_stride is None else v_head_stride, n_src, _p(src_index), w, sc,
                                  _ATTN_IMPL[0], _stream()))
+    if ev is not None:
+        ev[1].record()
+        ATTN_EVENTS.append((B, Nq, Nk, heads, d, sum(1 for x in weights if float(x) != 0.0), ev[0], ev[1]))
     LAUNCHES[0] += 1
     return out
 

@@ -40,8 +40,18 @@ def broadcast_shape(shape: Sequence[int], device, group: Optional[dist.ProcessGr
     return tuple(int(v) for v in t.tolist())
 
 
-def make_kv_gather(device, group: Optional[dist.ProcessGroup] = None):
-    """The reference-K/V exchange of this process group: NCCL all-gather (KVAllGather)."""
+def make_kv_gather(device, group: Optional[dist.ProcessGroup] = None, arena_bytes: Optional[int] = None):
+    """The reference-K/V exchange of this process group.  On CUDA: PeerKVAllGather - our own push + flag kernels over
+    NVLink peer memory (CUDA-graph capturable, gcb_allgather_ref_kv); if the peers' memory cannot be mapped (no IPC
+    between the processes) or GCB_KV_GATHER=nccl is set: KVAllGather (torch.distributed / NCCL, runs eagerly)."""
+    import os
+    dev = torch.device(device)
+    if dev.type == "cuda" and os.environ.get("GCB_KV_GATHER", "peer") != "nccl":
+        try:
+            return PeerKVAllGather(dev, group, arena_bytes or int(os.environ.get("GCB_PEER_ARENA_BYTES", 2 << 30)))
+        except Exception as exc:   # e.g. cudaIpcOpenMemHandle refused in a sandbox: keep running on NCCL, say so
+            import warnings
+            warnings.warn(f"peer-memory K/V exchange unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather")
     return KVAllGather(group)
 
 
@@ -86,16 +96,25 @@ def view_src_index(Bv: int, R: int, world: int, ref_frames: Sequence[int] = (0, 
 
 
 class KVAllGather:
-    """All-gather of the reference rows' fused q|k|v projection of one self-attention layer.
+    """All-gather of the reference rows' fused q|k|v projection of one self-attention layer (torch.distributed: NCCL on
+    GPUs, gloo in the CPU tests).  Not captured in CUDA graphs (`graph_capturable = False`).
 
     local [per, N, 3C] (rows beyond the rank's real rows are padding) -> gathered [world*per, N, 3C].  Output buffers
     are cached per layer so that captured CUDA graphs (and the view graphs that read them) see stable addresses."""
+
+    graph_capturable = False
 
     def __init__(self, group: Optional[dist.ProcessGroup] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.buffers: Dict[str, torch.Tensor] = {}
         self.bytes = 0
+
+    def begin_pass(self) -> None:   # NCCL collectives are ordered by the communicator: nothing to do
+        return None
+
+    def check(self) -> None:
+        return None
 
     def __call__(self, layer: str, local: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
@@ -108,6 +127,110 @@ class KVAllGather:
         dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
         self.bytes += out.numel() * out.element_size()
         return out
+
+
+class _ArenaView:
+    """Zero-copy torch view of a region of the peer arena (raw cudaMalloc memory) via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerKVAllGather:
+    """Same call contract as KVAllGather - `gather(layer, local [per, ...]) -> gathered [world*per, ...]` - on the
+    peer-memory kernels of csrc/peer.cu.  Regions of the arena are assigned per layer name on first use (every rank
+    issues the same sequence of calls, so offsets and flag slots agree without communication); the returned tensor
+    aliases the local arena, i.e. later kernels read the gathered K/V in place.  `begin_pass()` is the cross-rank
+    barrier that must precede re-writing regions the peers may still be reading (engine: once per sharded reference pass).
+    Everything is enqueued on the current stream and can be captured in a CUDA graph."""
+    graph_capturable = True
+
+    def __init__(self, device, group: Optional[dist.ProcessGroup] = None, arena_bytes: int = 2 << 30):
+        import ctypes
+        from ._lib import check, lib
+        self._lib, self._check = lib, check
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dev = torch.device(device)
+        self.arena_bytes = int(arena_bytes)
+        with torch.cuda.device(self.dev):
+            h = ctypes.c_void_p()
+            check(lib.gcb_handle_create(self.world, self.rank, self.arena_bytes, ctypes.byref(h)))
+            self.handle = h
+            mine = ctypes.create_string_buffer(64)
+            check(lib.gcb_handle_ipc_export(h, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine.raw), group=group)
+            ok = True
+            try:
+                for q in range(self.world):
+                    if q != self.rank:
+                        check(lib.gcb_handle_ipc_open(h, q, handles[q]))
+            except Exception:
+                ok = False
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok, group=group)     # all ranks take the same branch
+            if not all(flags):
+                lib.gcb_handle_destroy(h)
+                self.handle = None
+                raise RuntimeError("cudaIpcOpenMemHandle failed on at least one rank")
+        self.base = int(lib.gcb_handle_arena(self.handle))
+        self.cursor = int(lib.gcb_handle_control_bytes())
+        self.regions: Dict[str, Tuple[int, int, torch.Tensor, int]] = {}   # layer -> (offset, slot, view, bytes_per_rank)
+        self.bytes = 0
+        dist.barrier(group=group)
+
+    def _region(self, layer: str, local: torch.Tensor):
+        ent = self.regions.get(layer)
+        per_bytes = local.numel() * local.element_size()
+        if ent is None or ent[3] != per_bytes or tuple(ent[2].shape[1:]) != tuple(local.shape[1:]):
+            if local.dtype != torch.float16:
+                raise TypeError("PeerKVAllGather carries fp16 tensors")
+            if per_bytes % 16:
+                raise ValueError(f"{layer}: {per_bytes} bytes per rank is not a multiple of 16")
+            off = (self.cursor + 255) // 256 * 256
+            total = per_bytes * self.world
+            if off + total > self.arena_bytes:
+                raise MemoryError(f"peer arena of {self.arena_bytes} bytes exhausted at layer {layer} "
+                                  f"(set GCB_PEER_ARENA_BYTES)")
+            if ent is not None:
+                slot = ent[1]                      # same layer at a new shape: its flag slot carries over
+            else:
+                slot = 1 + len(self.regions)       # slot 0 is the pass barrier
+            if slot >= 128:
+                raise RuntimeError("more than 127 gathered buffers")
+            shape = (self.world * local.shape[0],) + tuple(local.shape[1:])
+            view = torch.as_tensor(_ArenaView(self.base + off, shape, "<f2"), device=self.dev)
+            self.cursor = off + total
+            ent = (off, slot, view, per_bytes)
+            self.regions[layer] = ent
+        return ent
+
+    def begin_pass(self) -> None:
+        self._check(self._lib.gcb_peer_barrier(self.handle, 0, torch.cuda.current_stream().cuda_stream))
+
+    def __call__(self, layer: str, local: torch.Tensor) -> torch.Tensor:
+        off, slot, view, per_bytes = self._region(layer, local)
+        src = local.contiguous()
+        self._check(self._lib.gcb_allgather_ref_kv(self.handle, off, src.data_ptr(), per_bytes, slot,
+                                                   torch.cuda.current_stream().cuda_stream))
+        self.bytes += per_bytes * self.world
+        return view
+
+    def check(self) -> None:
+        """Synchronous: raises if any wait of this rank timed out."""
+        import ctypes
+        err = ctypes.c_int(0)
+        self._check(self._lib.gcb_handle_error(self.handle, ctypes.byref(err)))
+        if err.value:
+            raise RuntimeError(f"peer all-gather timed out waiting on flag slot {err.value - 1}: a rank fell out of step")
+
+    def close(self) -> None:
+        if getattr(self, "handle", None) is not None:
+            self.regions.clear()
+            self._lib.gcb_handle_destroy(self.handle)
+            self.handle = None
 
 
 def gather_view_results(local: torch.Tensor, local_ids: Sequence[int], V: int, world: int,

@@ -203,6 +203,30 @@ int gcb_rasterize_rgbd_fwd(const float* xys, const float* conics, const float* r
                            int img_w, const float* d_background3, float* out_rgb, float* out_depth, float* out_alpha,
                            void* stream);
 
+/* ---- reference-K/V exchange over NVLink peer memory (the one collective of the path; replaces the
+ *      per-layer `ncclAllGather` a multi-GPU port of gc_pipeline.py:206-219 would issue).  One process per GPU; the
+ *      host side exchanges the 64-byte IPC handles once (e.g. torch.distributed.all_gather_object).  All calls enqueue
+ *      plain kernels on `stream` (CUDA-graph capturable, no host synchronisation). ---- */
+typedef struct gcb_handle gcb_handle_t;
+/* Bytes at the head of every arena reserved for flags / epochs: payload regions start at or after this offset. */
+size_t gcb_handle_control_bytes(void);
+/* Allocates this rank's arena (cudaMalloc on the current device, control block zeroed). */
+int gcb_handle_create(int world, int rank, size_t arena_bytes, gcb_handle_t** out);
+int gcb_handle_destroy(gcb_handle_t* handle);
+/* Local arena base (device pointer): the gathered blocks are read in place from here. */
+void* gcb_handle_arena(gcb_handle_t* handle);
+int gcb_handle_ipc_export(gcb_handle_t* handle, unsigned char* out64);
+int gcb_handle_ipc_open(gcb_handle_t* handle, int peer, const unsigned char* in64);
+/* All-gather: local_src (bytes_per_rank bytes, 16-byte aligned) lands at arena_offset + rank * bytes_per_rank in EVERY
+ * rank's arena; returns (in stream order) once every peer's block has arrived in the local arena.  `slot` (0..127)
+ * names the flag set; use one slot per concurrently live buffer. */
+int gcb_allgather_ref_kv(gcb_handle_t* handle, size_t arena_offset, const void* local_src, size_t bytes_per_rank, int slot,
+                         void* stream);
+/* Cross-rank barrier in stream order (guards the reuse of gathered blocks that peers still read). */
+int gcb_peer_barrier(gcb_handle_t* handle, int slot, void* stream);
+/* Synchronous: *out != 0 when a wait timed out (a peer never signalled); the gathered data is then invalid. */
+int gcb_handle_error(gcb_handle_t* handle, int* out);
+
 /* ---- backward (the 3DGS fine-tune step after the edit: gc_trainer.py:257-301 -> loss.backward() through gsplat's
  *      autograd Functions).  Exact derivatives of the forward kernels above. ---- */
 

@@ -1,5 +1,6 @@
-"""2-GPU test (NCCL): views sharded across ranks + reference pass sharded over its CFG rows with the per-layer K/V
-all-gather gives the SAME latents as the single-GPU run (every kernel is batch-invariant, the all-gather is exact)."""
+"""2-GPU test: views sharded across ranks + reference pass sharded over its CFG rows with the per-layer K/V all-gather
+gives the SAME latents as the single-GPU run (every kernel is batch-invariant, the all-gather is exact).  Needs a
+2-GPU box (`gpurun --gpus 2`); the same check runs inside `bench.py` at N > 1 (`extra.multi_gpu_check`)."""
 import os
 import socket
 
@@ -19,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, tmpdir, graph_refs):
+def _worker(rank, world, port, tmpdir, kind):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -39,7 +40,10 @@ def _worker(rank, world, port, tmpdir, graph_refs):
         pos, neg = torch.randn((1, 77, 768), generator=g), torch.randn((1, 77, 768), generator=g)
         ref_idx = [0, 3, 5, 8]
         eng = EditEngine(den, use_graphs=True)
-        ctx = {"world": world, "rank": rank, "gather": par.KVAllGather(), "graph_refs": graph_refs}
+        os.environ["GCB_KV_GATHER"] = kind
+        gather = par.make_kv_gather(f"cuda:{rank}", arena_bytes=256 << 20)
+        assert type(gather).__name__ == ("PeerKVAllGather" if kind == "peer" else "KVAllGather"), type(gather).__name__
+        ctx = {"world": world, "rank": rank, "gather": gather}
         mine = par.shard_views(V, world, rank, ref_idx)
         out = eng.edit_refs_once(lat, disp, ref_idx, pos, neg, S, guidance, view_batch=2, view_ids=mine, dist_ctx=ctx)
         full = par.gather_view_results(out[mine].contiguous(), mine, V, world)
@@ -55,11 +59,14 @@ def _worker(rank, world, port, tmpdir, graph_refs):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_edit_equals_single_gpu(tmp_path, graph_refs=False):
+@pytest.mark.parametrize("kind", ["peer", "nccl"])
+def test_two_gpu_sharded_edit_equals_single_gpu(tmp_path, kind):
+    """kind = "peer": gcb_allgather_ref_kv (our NVLink peer-memory kernels, captured in the reference pass's CUDA graph);
+    kind = "nccl": torch.distributed all-gather (eager)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), graph_refs), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), kind), nprocs=2, join=True)
     diff, nbytes = open(tmp_path / "result").read().split()
     assert float(diff) == 0.0, diff
     assert int(nbytes) > 0
