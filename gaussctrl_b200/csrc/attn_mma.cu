@@ -253,10 +253,9 @@ template <int D, int BN>
 int launch(const AttnParams& p, cudaStream_t st) {
     constexpr int DP = (D + 15) / 16 * 16, LDS = DP + 8;
     const size_t smem = (size_t)(BMQ + 4 * BN) * LDS * 2;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // one bit per device ordinal
+    if (gcb_first_use_on_device(configured)) {
         GCB_CUDA(cudaFuncSetAttribute(attn_mma_kernel<D, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     dim3 grid(gcb_cdiv(p.Nq, BMQ), p.heads, p.B);
     attn_mma_kernel<D, BN><<<grid, 128, smem, st>>>(p);

@@ -3,17 +3,21 @@
 //
 //   out[b, i, h, :] = sum_s w_s * softmax_j( q[b,i,h,:] . K_s[j,h,:] * scale ) V_s[j,h,:]      (utils.py:25-37, 88-117)
 //
-// One CTA = 256 query rows (two 128-row slots A/B) of one (batch row, head).  Warp roles (320 threads):
-//   warps 0-3 / 4-7 : softmax of slot A / B - one query row per thread, S read from TMEM (tcgen05.ld), exp2 on the
+// One CTA = NSLOT 128-row query slots of one (batch row, head).  Warp roles (32 * (4 NSLOT + 2) threads):
+//   warps 4t..4t+3  : softmax of slot t - one query row per thread, S read from TMEM (tcgen05.ld), exp2 on the
 //                     MUFU, row sums in fp32 registers, P written back to TMEM (tcgen05.st) as packed halves: the
 //                     A operand of P V.  Probabilities never touch shared memory or HBM.
-//   warp 8          : TMA producer (Q once; K and V tiles of BN keys through 4-stage mbarrier rings)
-//   warp 9          : TMEM allocator + tcgen05.mma issuer (one elected lane):
+//   warp 4 NSLOT    : TMA producer (Q once; K and V tiles of BN keys through mbarrier rings)
+//   warp 4 NSLOT + 1: TMEM allocator + tcgen05.mma issuer (one elected lane):
 //                       S   = Q K^T    M128 x N(BN) x K(DK)   both operands K-major, 128B-swizzled 64-column TMA boxes
 //                       O  += P V      M128 x N(NV) x K(BN)   A = P from TMEM, B = V MN-major straight from its row-major tile
-// Head dim 40: BN=128, DK=48 - the Q/K boxes are 64 columns wide; columns 40..47 of Q are zeroed in smem so the
-//   neighbouring head's columns that ride along in K contribute nothing; NV=48 (columns 40..47 of O are don't-care).
-// Head dim 80: BN=64, DK=80 (two boxes: 64 + 16 used columns), NV=80 (two MN atoms of V).
+// Head dim 40: two slots, BN=128, DK=48 - the Q/K boxes are 64 columns wide; columns 40..47 of Q are zeroed in smem so
+//   the neighbouring head's columns that ride along in K contribute nothing; NV=48 (columns 40..47 of O are don't-care).
+//   The kernel is bound by the MUFU (exp2: 16/clk/SM); each scheduler's MUFU is fed by the two softmax warps resident on
+//   it, one per slot.  Measured alternatives (profiles/r2_attn_ab.md): a third slot with BN=64 (TMEM: 3 x (64 S + 32 P +
+//   48 O) = 432 columns) runs at 405 TFLOP/s against 530 - and so does BN=64 with two slots, i.e. the per-tile fixed
+//   cost of the smaller tile eats the gain; a four-piece P store 495; issuing a slot's next QK^T after its own PV 442.
+// Head dim 80: two slots, BN=64, DK=80 (two boxes: 64 + 16 used columns), NV=80 (two MN atoms of V).
 // Online softmax with lazy rescaling (threshold 2^8): the O correction (TMEM load-scale-store) is rare.  Sources are
 // processed back to back; at the end of each source the slot folds O * w_s / l into an fp32 accumulator (shared
 // memory for d=40, TMEM for d=80 - whichever the budget of 512 columns / 227 KB leaves room for).
@@ -28,7 +32,6 @@ namespace {
 
 constexpr int MAX_SRC = 8;
 constexpr int BM = 128;  // query rows per slot
-constexpr int STAGES = 4;
 constexpr float RESCALE_THRESHOLD = 8.f;
 #ifndef GCB_ATTN_LAG
 #define GCB_ATTN_LAG 0
@@ -48,6 +51,14 @@ constexpr float RESCALE_THRESHOLD = 8.f;
 //             484.7 TFLOP/s alone, 535.7 with SPLIT_ST - no gain, the TMEM-load latency is not what the max phase waits on.
 //   SPLIT_ST = 4 (not measured yet - the round's GPU budget ended): four pieces of 16 packed registers; the extra block
 //             boundaries come from re-waiting the already completed p_free phase (returns at once, but is a branch).
+#ifndef GCB_ATTN_PINGPONG
+#define GCB_ATTN_PINGPONG 0
+#endif
+// MUFU ping-pong (two-slot kernels): the softmax warps of slot 0 and slot 1 that share a scheduler (same TMEM lane
+// quarter) pass a token through a pair of named barriers so that only ONE of them is in its exponential phase at a
+// time - the other does its non-MUFU work (wait for S, TMEM load, row max, pack, store) meanwhile.  Without it the two
+// exponential phases mostly coincide (each then runs at half the MUFU rate) and so do the non-MUFU phases (pipe idle).
+constexpr bool ATTN_PINGPONG = GCB_ATTN_PINGPONG != 0;
 constexpr bool ATTN_SPLIT_LD = GCB_ATTN_SPLIT_LD != 0, ATTN_SPLIT_ST = GCB_ATTN_SPLIT_ST != 0;
 constexpr bool ATTN_SPLIT_ST4 = GCB_ATTN_SPLIT_ST == 4;
 constexpr int ATTN_LAG = GCB_ATTN_LAG;  // 0 = off, 1 = slot 0 signals after its row max, 2 = after half of its exponentials
@@ -56,7 +67,16 @@ template <int D_>
 struct Cfg;
 template <>
 struct Cfg<40> {
-    static constexpr int D = 40, BN = 128, DK = 48, NV = 48, BOXES = 1;
+#if defined(GCB_ATTN40_THREE_SLOTS)   // A/B (r2j): three slots, BN = 64 - 405 TFLOP/s against 530 for the default
+    static constexpr int D = 40, BN = 64, DK = 48, NV = 48, BOXES = 1, NSLOT = 3, STAGES = 6;
+    static constexpr uint32_t TM_S = 0, TM_P = 192, TM_O = 288, TM_O_STRIDE = 48, TM_ACC = 0;
+#elif defined(GCB_ATTN40_BN64_TWO)    // A/B (r2j): BN = 64 with two slots - also 405: the tile size costs, not the slots
+    static constexpr int D = 40, BN = 64, DK = 48, NV = 48, BOXES = 1, NSLOT = 2, STAGES = 6;
+    static constexpr uint32_t TM_S = 0, TM_P = 192, TM_O = 288, TM_O_STRIDE = 48, TM_ACC = 0;
+#else
+    static constexpr int D = 40, BN = 128, DK = 48, NV = 48, BOXES = 1, NSLOT = 2, STAGES = 4;
+    static constexpr uint32_t TM_S = 0, TM_O = 256, TM_O_STRIDE = 64, TM_P = 384, TM_ACC = 0;
+#endif
     static constexpr bool ZERO_Q_PAD = true, ACC_IN_TMEM = false;
     // exponentials per 8 evaluated by the FMA-pipe polynomial instead of the MUFU.  Measured on B200 (r1): 3/8 makes
     // the kernel SLOWER (546 -> 485 TFLOP/s): 3-register FFMA/FADD issue at half rate per SM sub-partition, so the
@@ -67,11 +87,10 @@ struct Cfg<40> {
 #else
     static constexpr bool EXP_F16X2 = false;
 #endif
-    static constexpr uint32_t TM_S = 0, TM_O = 256, TM_O_STRIDE = 64, TM_P = 384, TM_ACC = 0;
 };
 template <>
 struct Cfg<80> {
-    static constexpr int D = 80, BN = 64, DK = 80, NV = 80, BOXES = 2;
+    static constexpr int D = 80, BN = 64, DK = 80, NV = 80, BOXES = 2, NSLOT = 2, STAGES = 4;
     static constexpr bool ZERO_Q_PAD = false, ACC_IN_TMEM = true;
     static constexpr int POLY_OF_8 = 0;
     static constexpr bool EXP_F16X2 = false;
@@ -95,13 +114,14 @@ template <int D_>
 struct __align__(1024) Smem {
     using C = Cfg<D_>;
     static constexpr uint32_t QBOX = BM * 128, KVBOX = C::BN * 128;
-    uint8_t q[2][C::BOXES][QBOX];
+    static constexpr int STAGES = C::STAGES, NSLOT = C::NSLOT;
+    uint8_t q[NSLOT][C::BOXES][QBOX];
     uint8_t k[STAGES][C::BOXES][KVBOX];
     uint8_t v[STAGES][C::BOXES][KVBOX];
-    float acc[C::ACC_IN_TMEM ? 1 : 2][C::ACC_IN_TMEM ? 1 : C::D][C::ACC_IN_TMEM ? 4 : BM];  // [slot][column][row]
+    float acc[C::ACC_IN_TMEM ? 1 : NSLOT][C::ACC_IN_TMEM ? 1 : C::D][C::ACC_IN_TMEM ? 4 : BM];  // [slot][column][row]
     uint64_t q_full, q_ready;
     uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-    uint64_t s_full[2], s_free[2], p_ready[2], p_free[2], o_free[2];
+    uint64_t s_full[NSLOT], s_free[NSLOT], p_ready[NSLOT], p_free[NSLOT], o_free[NSLOT];
     uint64_t lag_bar;
     uint32_t tmem_base;
 };
@@ -146,6 +166,12 @@ __device__ __forceinline__ void lag_arrive(uint32_t bar, uint32_t dep) {
         "mbarrier.arrive.shared::cta.b64 _, [a];\n\t}"
         ::"r"(bar), "r"(dep)
         : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
@@ -195,13 +221,14 @@ __device__ __forceinline__ void tmem_st16_from(uint32_t taddr, const uint32_t (&
 }
 
 template <int D_>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(32 * (4 * Cfg<D_>::NSLOT + 2), 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
                const __grid_constant__ CUtensorMap tmV2, const AttnTcParams p) {
     using C = Cfg<D_>;
     using SM = Smem<D_>;
-    constexpr int D = C::D, BN = C::BN, BOXES = C::BOXES;
+    constexpr int D = C::D, BN = C::BN, BOXES = C::BOXES, NSLOT = C::NSLOT, STAGES = C::STAGES;
+    constexpr int W_TMA = 4 * NSLOT, W_MMA = 4 * NSLOT + 1;
     constexpr int KSTEPS = C::DK / 16, PV_STEPS = BN / 16, PCOLS = BN / 2;
     constexpr uint32_t STAGE_BYTES = BOXES * SM::KVBOX;
     extern __shared__ uint8_t smem_raw[];
@@ -210,17 +237,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int nkt = p.Nk / BN;
     const int T = p.n_act * nkt;  // (source, key tile) pairs, processed in order
+    // the last CTA of a (row, head) may own fewer than NSLOT slots (Nq is a multiple of 128, not of NSLOT * 128)
+    const int nslot = min(NSLOT, p.Nq / BM - qt * NSLOT);
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&sm.q_full), 1);
-        mbar_init(smem_u32(&sm.q_ready), 256);
+        mbar_init(smem_u32(&sm.q_ready), 128 * nslot);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(smem_u32(&sm.k_full[i]), 1);
             mbar_init(smem_u32(&sm.k_empty[i]), 1);
             mbar_init(smem_u32(&sm.v_full[i]), 1);
             mbar_init(smem_u32(&sm.v_empty[i]), 1);
         }
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < NSLOT; ++t) {
             mbar_init(smem_u32(&sm.s_full[t]), 1);
             mbar_init(smem_u32(&sm.s_free[t]), 128);
             mbar_init(smem_u32(&sm.p_ready[t]), 128);
@@ -230,7 +259,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_init(smem_u32(&sm.lag_bar), 128);
         mbar_fence_init();
     }
-    if (warp == 9) {
+    if (warp == W_MMA) {
         tmem_alloc(smem_u32(&sm.tmem_base), 512);
         tmem_relinquish();
     }
@@ -239,7 +268,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
-    if (warp == 8) {
+    if (warp == W_TMA) {
         // ===================================================================== TMA producer (whole warp walks the loop,
         // one elected lane issues)
         if (elect_one_sync()) {
@@ -247,10 +276,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tma_prefetch_desc(&tmK);
             tma_prefetch_desc(&tmV);
             const uint32_t qf = smem_u32(&sm.q_full);
-            mbar_expect_tx(qf, 2 * BOXES * SM::QBOX);
-            const int qrow = b * p.Nq + qt * 2 * BM;
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
+            mbar_expect_tx(qf, nslot * BOXES * SM::QBOX);
+            const int qrow = b * p.Nq + qt * NSLOT * BM;
+            for (int t = 0; t < nslot; ++t)
 #pragma unroll
                 for (int bx = 0; bx < BOXES; ++bx)
                     tma_load_2d(smem_u32(sm.q[t][bx]), &tmQ, qf, head * D + bx * 64, qrow + t * BM);
@@ -282,7 +310,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             __syncwarp();
         }
-    } else if (warp == 9) {
+    } else if (warp == W_MMA) {
         // ===================================================================== MMA issuer (whole warp waits, one elected
         // lane issues tcgen05.mma / tcgen05.commit)
         const uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
@@ -303,7 +331,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tc_mma_ss(tmem + C::TM_S + (uint32_t)(t * BN), qd, kd, idesc_qk, (uint32_t)(ks != 0));
                 }
                 tc_commit(smem_u32(&sm.s_full[t]));
-                if (t == 1) tc_commit(smem_u32(&sm.k_empty[st]));
+                if (t == nslot - 1) tc_commit(smem_u32(&sm.k_empty[st]));
             }
             __syncwarp();
         };
@@ -323,12 +351,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int kk = 0; kk < PV_STEPS; ++kk)
                     tc_mma_ts(o_t, p_t + (uint32_t)(kk * 8), vd0 + (uint64_t)(kk * 128), idesc_pv, (uint32_t)((j | kk) != 0));
                 tc_commit(smem_u32(&sm.p_free[t]));
-                if (t == 1) tc_commit(smem_u32(&sm.v_empty[st]));
+                if (t == nslot - 1) tc_commit(smem_u32(&sm.v_empty[st]));
             }
             __syncwarp();
         };
-        issue_qk(0, 0);
-        issue_qk(1, 0);
+        for (int t = 0; t < nslot; ++t) issue_qk(t, 0);
         // Issue order.  qk(1, i+1) sits behind pv(0, i), which blocks until slot 0 has finished the exponentials of tile
         // i: slot 1 therefore starts every tile a fixed lag after slot 0.  That coupling is deliberate - with both QK^T
         // products issued ahead of the PVs (tried in r1j) the slots fall into step, their non-MUFU phases coincide and
@@ -338,15 +365,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // 729 -> 535 at d=80.  The round-1 order below is the measured optimum of the three; kept at 0.
         if (ATTN_LAG) mbar_wait(smem_u32(&sm.lag_bar), 0);
         for (int i = 0; i < T; ++i) {
-            if (i + 1 < T) issue_qk(0, i + 1);
-            issue_pv(0, i);
-            if (i + 1 < T) {
-                if (ATTN_LAG) mbar_wait(smem_u32(&sm.lag_bar), ((uint32_t)(i + 1)) & 1u);
-                issue_qk(1, i + 1);
+#if defined(GCB_ATTN_ORDER) && GCB_ATTN_ORDER == 1
+            // A/B: slot t's next QK^T goes out right after ITS OWN PV (it only needs s_free, signalled early in the tile)
+            for (int t = 0; t < nslot; ++t) {
+                issue_pv(t, i);
+                if (i + 1 < T) issue_qk(t, i + 1);
             }
-            issue_pv(1, i);
+#else
+            for (int t = 0; t < nslot; ++t) {
+                if (i + 1 < T) {
+                    if (ATTN_LAG && t == 1) mbar_wait(smem_u32(&sm.lag_bar), ((uint32_t)(i + 1)) & 1u);
+                    issue_qk(t, i + 1);
+                }
+                issue_pv(t, i);
+            }
+#endif
         }
-    } else {
+    } else if ((warp >> 2) < nslot) {
         // ===================================================================== softmax slots
         const int t = warp >> 2;         // slot
         const int wq = warp & 3;         // TMEM lane quarter
@@ -365,6 +400,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             fence_proxy_async();
         }
         mbar_arrive(smem_u32(&sm.q_ready));
+        // named barriers 1..8: "slot t, quarter wq may run its exponentials"; slot 0 goes first
+        const bool pingpong = ATTN_PINGPONG && NSLOT == 2 && nslot == 2;
+        const uint32_t bar_mine = 1u + (uint32_t)(t * 4 + wq), bar_other = 1u + (uint32_t)((t ^ 1) * 4 + wq);
+        if (pingpong && t == 1) named_bar_arrive(bar_other, 64);
 
         for (int s = 0; s < p.n_act; ++s) {
             float m = -INFINITY;  // running reference max, exp2 domain
@@ -507,6 +546,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     l += (l0 + l1) + (l2 + l3);
                     tmem_st16_from<(BN == 128 ? 48 : 0)>(p_t + 48, sr);
                 } else if (ATTN_SPLIT_ST && BN == 128) {
+                    if (pingpong) named_bar_sync(bar_mine, 64);
                     exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 4>{});   // keys 0..63
                     if (!waited) {
                         mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
@@ -514,8 +554,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     }
                     tmem_st32_from<0>(p_t, sr);                                                   // packed pairs 0..31
                     exp_block(integral_constant<int, BN / 4>{}, integral_constant<int, BN / 2>{});  // keys 64..127
+                    // hand the MUFU to the paired warp (slot 1 keeps the token after its very last tile: slot 0 is done)
+                    if (pingpong && !(t == 1 && i == T - 1)) named_bar_arrive(bar_other, 64);
                     l += (l0 + l1) + (l2 + l3);
                     tmem_st32_from<(BN == 128 ? 32 : 0)>(p_t + 32, sr);
+                } else if (ATTN_SPLIT_ST && BN == 64) {
+                    if (pingpong) named_bar_sync(bar_mine, 64);
+                    exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 4>{});   // keys 0..31
+                    if (!waited) {
+                        mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
+                        tc_fence_after();
+                    }
+                    tmem_st16_from<0>(p_t, sr);                                                   // packed pairs 0..15
+                    exp_block(integral_constant<int, BN / 4>{}, integral_constant<int, BN / 2>{});  // keys 32..63
+                    if (pingpong && !(t == 1 && i == T - 1)) named_bar_arrive(bar_other, 64);
+                    l += (l0 + l1) + (l2 + l3);
+                    tmem_st16_from<(BN == 64 ? 16 : 0)>(p_t + 16, sr);
                 } else {
                 exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 2>{});
                 if (ATTN_LAG == 2 && t == 0) lag_arrive(smem_u32(&sm.lag_bar), sr[BN / 4 - 1]);
@@ -566,7 +620,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_arrive(smem_u32(&sm.o_free[t]));
         }
         // ---- store the row: D halves = D/8 x 16 B
-        const long long grow_ = (long long)b * p.Nq + qt * 2 * BM + t * BM + row;
+        const long long grow_ = (long long)b * p.Nq + (qt * NSLOT + t) * BM + row;
         uint4* dst = reinterpret_cast<uint4*>(p.out + grow_ * p.ld_out + head * D);
 #pragma unroll
         for (int c = 0; c < (D + 15) / 16; ++c) {
@@ -596,7 +650,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem, 512);
+    if (warp == W_MMA) tmem_dealloc(tmem, 512);
 }
 
 int encode_rows(CUtensorMap* tm, const void* base, int ld, long long rows, int width, int box_rows) {
@@ -631,13 +685,12 @@ int launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, con
         tmV2 = tmV;
     }
     const size_t smem = sizeof(Smem<D_>) + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // one bit per device ordinal
+    if (gcb_first_use_on_device(configured)) {
         GCB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
-    dim3 grid(Nq / (2 * BM), heads, B);
-    attn_tc_kernel<D_><<<grid, 320, smem, stream>>>(tmQ, tmK, tmV, tmK2, tmV2, p);
+    dim3 grid((Nq / BM + C::NSLOT - 1) / C::NSLOT, heads, B);
+    attn_tc_kernel<D_><<<grid, 32 * (4 * C::NSLOT + 2), smem, stream>>>(tmQ, tmK, tmV, tmK2, tmV2, p);
     GCB_LAUNCH_CHECK();
     return GCB_OK;
 }
@@ -646,7 +699,7 @@ int launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, con
 
 int gcb_attn_tc_supported(int Nq, int Nk, int heads, int d) {
     (void)heads;
-    if (Nq % (2 * BM) != 0) return 0;
+    if (Nq % BM != 0) return 0;
     if (d == 40) return Nk % Cfg<40>::BN == 0 && Nk >= Cfg<40>::BN;
     if (d == 80) return Nk % Cfg<80>::BN == 0 && Nk >= Cfg<80>::BN;
     return 0;

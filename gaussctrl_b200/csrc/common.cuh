@@ -43,6 +43,17 @@ void gcb_set_error(const char* fmt, ...);
 
 static inline int gcb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int gcb_sm_count();
+// cudaFuncSetAttribute is per DEVICE: "configure once" state is a bit mask over device ordinals, not one process-wide
+// flag (a process that drives two GPUs must configure each of them).  Returns true the first time it is called for
+// the current device with this mask.
+static inline bool gcb_first_use_on_device(unsigned long long& mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    const unsigned long long bit = 1ull << dev;
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
 
 // ---------------------------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

@@ -500,11 +500,9 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
         }
     }
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-    static size_t configured_smem = 0;
-    if (smem > configured_smem) {
+    static unsigned long long configured = 0;   // one bit per device ordinal
+    if (gcb_first_use_on_device(configured))
         GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        configured_smem = 225 * 1024;
-    }
     dim3 grid(gcb_cdiv(Cout, p.BN), gcb_cdiv(M, BM));
     gemm_tc_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p);
     GCB_LAUNCH_CHECK();

@@ -489,10 +489,9 @@ extern "C" int gcb_sh_fwd(int degree, int K, const float* viewdirs, const float*
                   degree, K);
     if (N == 0) return GCB_OK;
     const size_t smem = (size_t)8 * 32 * (K * 3 + 1) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // one bit per device ordinal
+    if (gcb_first_use_on_device(configured)) {
         GCB_CUDA(cudaFuncSetAttribute(sh_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        configured = true;
     }
     sh_fwd_kernel<<<gcb_cdiv(N, 256), 256, smem, ST>>>(degree, K, viewdirs, coeffs, colors, N);
     GCB_LAUNCH_CHECK();
