@@ -482,7 +482,7 @@ def main():
             from gaussctrl_b200.diffusion import cached_crossview_plan
             from gaussctrl_b200.gc_pipeline import crossview_ref_frames
             key = next(k for k in pipe.engine._steps if k[0] == "refs_once")
-            ref_step, rec, view_step = pipe.engine._steps[key]
+            view_step = pipe.engine._steps[key][2][0]
             ops.ATTN_EVENTS = []
             marks = []
             for _ in range(3):

@@ -23,14 +23,18 @@ class _GraphedStep:
     """One denoising step for a fixed batch shape as a CUDA graph: x <- ddim(x, eps(x, t, cond))."""
 
     def __init__(self, den: SD15Denoiser, n_lat: int, cfg: bool, guidance: float, plan: AttnPlan, hw: int,
-                 use_graph: bool):
+                 use_graph: bool, share: Optional["_GraphedStep"] = None):
         dev = den.dev
         self.den, self.cfg, self.guidance, self.plan, self.n_lat = den, cfg, guidance, plan, n_lat
         B = 2 * n_lat if cfg else n_lat
-        self.x = torch.zeros((n_lat, hw, hw, 4), dtype=torch.float16, device=dev)
-        self.cond = torch.zeros((B, hw, hw, den.ch[0]), dtype=torch.float16, device=dev)
-        self.t = torch.zeros((B,), dtype=torch.float32, device=dev)
-        self.coef = torch.zeros((4,), dtype=torch.float32, device=dev)
+        if share is not None:
+            # a second graph over the SAME state (double-buffered reference pass: only the recorded K/V differ)
+            self.x, self.cond, self.t, self.coef = share.x, share.cond, share.t, share.coef
+        else:
+            self.x = torch.zeros((n_lat, hw, hw, 4), dtype=torch.float16, device=dev)
+            self.cond = torch.zeros((B, hw, hw, den.ch[0]), dtype=torch.float16, device=dev)
+            self.t = torch.zeros((B,), dtype=torch.float32, device=dev)
+            self.coef = torch.zeros((4,), dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
         self.launches = 0
@@ -51,9 +55,16 @@ class _GraphedStep:
         if self.cfg:
             self.cond[n:].copy_(cond_emb)
 
-    def run(self, t: int, coefs: Sequence[float]) -> None:
-        self.t.fill_(float(t))
-        self.coef.copy_(torch.tensor(coefs, dtype=torch.float32), non_blocking=False)
+    def run(self, t, coefs) -> None:
+        """t / coefs: DEVICE tensors (1 and 4 floats, rows of EditEngine._schedule_tables) - copied device-to-device, so
+        the host never waits for the stream (it enqueues the whole loop ahead; needed for the two-stream overlap of the
+        reference pass with the view batches) - or plain Python numbers (host copy, synchronous)."""
+        if isinstance(t, torch.Tensor):
+            self.t.copy_(t.reshape(1).expand_as(self.t))
+            self.coef.copy_(coefs)
+        else:
+            self.t.fill_(float(t))
+            self.coef.copy_(torch.tensor(coefs, dtype=torch.float32), non_blocking=False)
         if not self.use_graph:
             self._body()
             return
@@ -82,7 +93,7 @@ class _ShardedRefStep:
     eps rows (32 KB each) and applies the CFG combine + DDIM update to all R latents."""
 
     def __init__(self, den: SD15Denoiser, R: int, guidance: float, hw: int, world: int, rank: int, gather,
-                 ref_frames: Sequence[int], use_graph: bool):
+                 ref_frames: Sequence[int], use_graph: bool, share: Optional["_ShardedRefStep"] = None):
         from . import parallel as par
         dev = den.dev
         self.den, self.R, self.guidance, self.world, self.rank = den, R, guidance, world, rank
@@ -98,10 +109,13 @@ class _ShardedRefStep:
                              [0.0] + [1.0 / K] * K, record_kv=self.rec,
                              text_index=torch.tensor([[g // R] for g in rows], dtype=torch.int32, device=dev),
                              gather=gather)
-        self.x = torch.zeros((R, hw, hw, 4), dtype=torch.float16, device=dev)
-        self.cond_all = torch.zeros((R, hw, hw, den.ch[0]), dtype=torch.float16, device=dev)
-        self.t = torch.zeros((self.per,), dtype=torch.float32, device=dev)
-        self.coef = torch.zeros((4,), dtype=torch.float32, device=dev)
+        if share is not None:
+            self.x, self.cond_all, self.t, self.coef = share.x, share.cond_all, share.t, share.coef
+        else:
+            self.x = torch.zeros((R, hw, hw, 4), dtype=torch.float16, device=dev)
+            self.cond_all = torch.zeros((R, hw, hw, den.ch[0]), dtype=torch.float16, device=dev)
+            self.t = torch.zeros((self.per,), dtype=torch.float32, device=dev)
+            self.coef = torch.zeros((4,), dtype=torch.float32, device=dev)
         self.gather = gather
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -123,13 +137,45 @@ class _ShardedRefStep:
     run = _GraphedStep.run
 
 
+class _ParityGather:
+    """The K/V exchange seen by one of the two double-buffered reference-pass graphs: same exchange object, region /
+    flag-slot names tagged with the buffer parity."""
+
+    def __init__(self, gather, parity: int):
+        self.inner, self.tag = gather, f"#p{parity}"
+        self.graph_capturable = bool(getattr(gather, "graph_capturable", False))
+
+    def __call__(self, layer: str, local: torch.Tensor) -> torch.Tensor:
+        return self.inner(layer + self.tag, local)
+
+    def begin_pass(self) -> None:
+        self.inner.begin_pass()
+
+    def check(self) -> None:
+        self.inner.check()
+
+
 class EditEngine:
-    def __init__(self, denoiser: SD15Denoiser, tables: Optional[DDIMTables] = None, use_graphs: bool = True):
+    def __init__(self, denoiser: SD15Denoiser, tables: Optional[DDIMTables] = None, use_graphs: bool = True,
+                 overlap_refs: Optional[bool] = None):
         self.den = denoiser
         self.dev = denoiser.dev
         self.tables = tables or DDIMTables()
         self.use_graphs = use_graphs
+        # refs_once schedule: run the reference pass one step AHEAD of the view batches on its own stream (double-buffered
+        # K/V).  The reference trajectory never depends on the other views, its pass is small (2R CFG rows, or 2R/N rows
+        # per rank) and leaves most SMs idle - on several GPUs it also waits on 23 exchanges per step; overlapped, the view
+        # batches fill those gaps.  GCB_REF_OVERLAP=0 turns it off.
+        import os
+        self.overlap_refs = (os.environ.get("GCB_REF_OVERLAP", "1") != "0") if overlap_refs is None else overlap_refs
+        self._ref_stream: Optional[torch.cuda.Stream] = None
         self._steps: Dict[tuple, object] = {}  # captured graphs are reused across calls (static buffers inside)
+
+    def _schedule_tables(self, ts: Sequence[int], coef_fn) -> tuple:
+        """Device tables of the timesteps [n] and of the four scheduler coefficients per step [n, 4] (one upload)."""
+        t_tab = torch.tensor([float(t) for t in ts], dtype=torch.float32).to(self.dev, non_blocking=True)
+        c_tab = torch.tensor([list(coef_fn(t)) for t in ts], dtype=torch.float32).to(self.dev, non_blocking=True)
+        return t_tab, c_tab
 
     # ------------------------------------------------------------------------------------------ helpers
     def _latents_in(self, z_nchw: torch.Tensor) -> torch.Tensor:
@@ -156,6 +202,7 @@ class EditEngine:
         x_all = self._latents_in(z0)
         out = torch.empty_like(x_all)
         ts = self.tables.inverse_timesteps(S)
+        t_tab, c_tab = self._schedule_tables(ts, lambda t: self.tables.inverse_step_coefs(t, S))
         for i in range(0, V, batch):
             n = min(batch, V - i)
             key = ("invert", n, hw)
@@ -164,8 +211,8 @@ class EditEngine:
             st = self._steps[key]
             st.x.copy_(x_all[i:i + n])
             st.set_cond(cond[i:i + n])
-            for t in ts:
-                st.run(t, self.tables.inverse_step_coefs(t, S))
+            for si in range(len(ts)):
+                st.run(t_tab[si], c_tab[si])
             out[i:i + n].copy_(st.x)
         return ops.nhwc_to_nchw(out)
 
@@ -187,8 +234,10 @@ class EditEngine:
         st = self._steps[key]
         st.x.copy_(self._latents_in(latents))
         st.set_cond(self._cond_emb(disparity))
-        for t in list(self.tables.timesteps(S))[:stop_after]:  # stop_after: parity tests truncate long schedules
-            st.run(t, self.tables.step_coefs(t, S))
+        ts = list(self.tables.timesteps(S))[:stop_after]  # stop_after: parity tests truncate long schedules
+        t_tab, c_tab = self._schedule_tables(ts, lambda t: self.tables.step_coefs(t, S))
+        for si in range(len(ts)):
+            st.run(t_tab[si], c_tab[si])
         return ops.nhwc_to_nchw(st.x[num_ref:].contiguous())
 
     @torch.no_grad()
@@ -221,21 +270,32 @@ class EditEngine:
         n_batches = max(1, -(-len(non_ref) // max(1, view_batch)))
         bsz = max(1, -(-len(non_ref) // n_batches))
         world = dist_ctx["world"] if dist_ctx else 1
-        key = ("refs_once", R, bsz, hw, float(guidance), tuple(ref_frames), world)
+        # P = 2: reference pass on its own stream, one step ahead of the views, K/V double-buffered by step parity
+        P = 2 if (self.overlap_refs and self.use_graphs and self.dev.type == "cuda") else 1
+        key = ("refs_once", R, bsz, hw, float(guidance), tuple(ref_frames), world, P)
         if key not in self._steps:
-            if world > 1:
-                # our peer-memory exchange is plain kernels and is captured with the rest of the pass; the NCCL
-                # all-gather stays eager (capturing it deadlocked on the 2-GPU box in round 1)
-                capturable = bool(getattr(dist_ctx["gather"], "graph_capturable", False))
-                rs = _ShardedRefStep(self.den, R, guidance, hw, world, dist_ctx["rank"], dist_ctx["gather"], ref_frames,
-                                     self.use_graphs and dist_ctx.get("graph_refs", capturable))
-                self._steps[key] = [rs, rs.rec, None]
-            else:
-                rec0: Dict[str, torch.Tensor] = {}
-                self._steps[key] = [_GraphedStep(self.den, R, True, guidance,
-                                                 literal_crossview_plan(R, self.dev, ref_frames, record_kv=rec0), hw,
-                                                 self.use_graphs), rec0, None]
-        ref_step, rec, view_step = self._steps[key]
+            refs_p: List[object] = []
+            recs_p: List[Dict[str, torch.Tensor]] = []
+            for par_i in range(P):
+                share = refs_p[0] if refs_p else None
+                if world > 1:
+                    # our peer-memory exchange is plain kernels and is captured with the rest of the pass; the NCCL
+                    # all-gather stays eager (capturing it deadlocked on the 2-GPU box in round 1)
+                    capturable = bool(getattr(dist_ctx["gather"], "graph_capturable", False))
+                    gather = _ParityGather(dist_ctx["gather"], par_i) if P > 1 else dist_ctx["gather"]
+                    rs = _ShardedRefStep(self.den, R, guidance, hw, world, dist_ctx["rank"], gather, ref_frames,
+                                         self.use_graphs and dist_ctx.get("graph_refs", capturable), share=share)
+                    refs_p.append(rs)
+                    recs_p.append(rs.rec)
+                else:
+                    rec_i: Dict[str, torch.Tensor] = {}
+                    refs_p.append(_GraphedStep(self.den, R, True, guidance,
+                                               literal_crossview_plan(R, self.dev, ref_frames, record_kv=rec_i), hw,
+                                               self.use_graphs, share=share))
+                    recs_p.append(rec_i)
+            self._steps[key] = [refs_p, recs_p, [None] * P]
+        ref_steps, recs, view_steps = self._steps[key]
+        ref_step = ref_steps[0]
         ref_step.x.copy_(x_all[list(ref_indices)])
         ref_step.set_cond(torch.stack([cond_map[v] for v in ref_indices]))
         # (2) view batches (the last one is padded by repeating its final view so one graph serves all)
@@ -246,22 +306,47 @@ class EditEngine:
             padded = b + [b[-1]] * (bsz - len(b))
             x_views.append(x_all[padded].clone())
             conds.append(torch.stack([cond_map[v] for v in padded]))
-        for t in list(self.tables.timesteps(S))[:stop_after]:
-            coefs = self.tables.step_coefs(t, S)
-            ref_step.run(t, coefs)
-            if batches and view_step is None:
-                vplan = cached_crossview_plan(bsz, R, self.dev, rec, ref_frames)
+        ts = list(self.tables.timesteps(S))[:stop_after]
+        t_tab, c_tab = self._schedule_tables(ts, lambda t: self.tables.step_coefs(t, S))
+        main = torch.cuda.current_stream() if self.dev.type == "cuda" else None
+        if P > 1:
+            if self._ref_stream is None:
+                self._ref_stream = torch.cuda.Stream(self.dev)
+            ref_stream = self._ref_stream
+            ref_stream.wait_stream(main)          # the reference latents / conditioning set above
+            ev_ref = [torch.cuda.Event() for _ in ts]
+            ev_view = [torch.cuda.Event() for _ in ts]
+        for si in range(len(ts)):
+            par_i = si % P
+            if P > 1:
+                with torch.cuda.stream(ref_stream):
+                    if si >= P:
+                        ref_stream.wait_event(ev_view[si - P])   # the views of step si-2 have finished reading this buffer
+                    ref_steps[par_i].run(t_tab[si], c_tab[si])
+                    ev_ref[si].record(ref_stream)
+                main.wait_event(ev_ref[si])
+            else:
+                ref_steps[0].run(t_tab[si], c_tab[si])
+            if batches and view_steps[par_i] is None:
+                vplan = cached_crossview_plan(bsz, R, self.dev, recs[par_i], ref_frames)
                 if world > 1:
                     from . import parallel as par
                     vplan.src_index = torch.tensor(par.view_src_index(bsz, R, world, ref_frames), dtype=torch.int32,
                                                    device=self.dev)
-                view_step = _GraphedStep(self.den, bsz, True, guidance, vplan, hw, self.use_graphs)
-                self._steps[key][2] = view_step
+                view_steps[par_i] = _GraphedStep(self.den, bsz, True, guidance, vplan, hw, self.use_graphs,
+                                                 share=view_steps[0])
+            view_step = view_steps[par_i]
             for bi in range(len(batches)):
-                view_step.x.copy_(x_views[bi])
-                view_step.set_cond(conds[bi])
-                view_step.run(t, coefs)
-                x_views[bi].copy_(view_step.x)
+                if len(batches) > 1 or si == 0:
+                    view_step.x.copy_(x_views[bi])
+                    view_step.set_cond(conds[bi])
+                view_step.run(t_tab[si], c_tab[si])
+                if len(batches) > 1 or si == len(ts) - 1:
+                    x_views[bi].copy_(view_step.x)
+            if P > 1:
+                ev_view[si].record(main)
+        if P > 1:
+            main.wait_stream(ref_stream)
         if world > 1:
             dist_ctx["gather"].check()   # one synchronisation per edit: did every wait of the K/V exchange complete?
         out = torch.zeros_like(x_all)

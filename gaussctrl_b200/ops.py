@@ -113,9 +113,6 @@ def geglu_perm(cout: int, device) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ norms
-_GN_WS = {}
-
-
 def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, groups: int,
               eps: float, silu: bool) -> torch.Tensor:
     """y = act(GN(cat(x1, x2, dim=-1))) over [B, H, W, C1(+C2)]."""
@@ -124,12 +121,11 @@ def groupnorm(x1: torch.Tensor, x2: Optional[torch.Tensor], gamma: torch.Tensor,
     HW = x1.numel() // (B * C1)
     C2 = 0 if x2 is None else x2.shape[-1]
     y = torch.empty(tuple(x1.shape[:-1]) + (C1 + C2,), dtype=torch.float16, device=x1.device)
+    # the statistics workspace is allocated per call: inside a CUDA-graph capture it then belongs to THAT graph's pool.
+    # (A workspace cached per stream was shared by every graph captured on torch's capture stream: two graphs replayed
+    # concurrently raced on it, and it dangled once the graph whose pool owned it was destroyed.)
     nbytes = lib.gcb_groupnorm_workspace_bytes(B, groups)
-    key = (x1.device, torch.cuda.current_stream().cuda_stream)
-    ws = _GN_WS.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=x1.device)
-        _GN_WS[key] = ws
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x1.device)
     check(lib.gcb_groupnorm_nhwc_fwd(_p(x1), _p(x2), _p(gamma), _p(beta), _p(y), B, HW, C1, C2, groups, eps, int(silu),
                                      _p(ws), ws.numel(), _stream()))
     LAUNCHES[0] += 2

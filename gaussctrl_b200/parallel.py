@@ -48,7 +48,7 @@ def make_kv_gather(device, group: Optional[dist.ProcessGroup] = None, arena_byte
     dev = torch.device(device)
     if dev.type == "cuda" and os.environ.get("GCB_KV_GATHER", "peer") != "nccl":
         try:
-            return PeerKVAllGather(dev, group, arena_bytes or int(os.environ.get("GCB_PEER_ARENA_BYTES", 2 << 30)))
+            return PeerKVAllGather(dev, group, arena_bytes or int(os.environ.get("GCB_PEER_ARENA_BYTES", 6 << 30)))
         except Exception as exc:   # e.g. cudaIpcOpenMemHandle refused in a sandbox: keep running on NCCL, say so
             import warnings
             warnings.warn(f"peer-memory K/V exchange unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather")
@@ -145,7 +145,7 @@ class PeerKVAllGather:
     Everything is enqueued on the current stream and can be captured in a CUDA graph."""
     graph_capturable = True
 
-    def __init__(self, device, group: Optional[dist.ProcessGroup] = None, arena_bytes: int = 2 << 30):
+    def __init__(self, device, group: Optional[dist.ProcessGroup] = None, arena_bytes: int = 6 << 30):
         import ctypes
         from ._lib import check, lib
         self._lib, self._check = lib, check
@@ -221,6 +221,7 @@ class PeerKVAllGather:
     def check(self) -> None:
         """Synchronous: raises if any wait of this rank timed out."""
         import ctypes
+        torch.cuda.synchronize(self.dev)      # the flag is read with a blocking copy that does not order with torch's streams
         err = ctypes.c_int(0)
         self._check(self._lib.gcb_handle_error(self.handle, ctypes.byref(err)))
         if err.value:

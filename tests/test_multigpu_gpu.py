@@ -41,7 +41,7 @@ def _worker(rank, world, port, tmpdir, kind):
         ref_idx = [0, 3, 5, 8]
         eng = EditEngine(den, use_graphs=True)
         os.environ["GCB_KV_GATHER"] = kind
-        gather = par.make_kv_gather(f"cuda:{rank}", arena_bytes=256 << 20)
+        gather = par.make_kv_gather(f"cuda:{rank}", arena_bytes=1 << 30)
         assert type(gather).__name__ == ("PeerKVAllGather" if kind == "peer" else "KVAllGather"), type(gather).__name__
         ctx = {"world": world, "rank": rank, "gather": gather}
         mine = par.shard_views(V, world, rank, ref_idx)
