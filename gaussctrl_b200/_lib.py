@@ -58,6 +58,9 @@ SIGNATURES = {
     "gcb_bin_gaussians": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_longlong, _P, _P, _P, _P, _P, c_size_t, _P]),
     "gcb_rasterize_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _FP, _P, _P, _P, _P]),
     "gcb_rasterize_rgbd_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
+    "gcb_render_eval_batch_workspace_bytes": (c_size_t, [c_int, c_longlong, c_int, c_int]),
+    "gcb_render_eval_batch": (c_int, [_P] * 6 + [c_int, c_int, c_int, _FP, _FP, _FP, _FP, c_int, c_int, _P, c_longlong,
+                                      _P, _P, _P, _P, _P, c_size_t, _P]),
     "gcb_handle_control_bytes": (c_size_t, []),
     "gcb_handle_create": (c_int, [c_int, c_int, c_size_t, POINTER(_P)]),
     "gcb_handle_destroy": (c_int, [_P]),

@@ -554,3 +554,77 @@ extern "C" int gcb_raster_finalize(const float* img4, const float* final_T, floa
     GCB_LAUNCH_CHECK();
     return GCB_OK;
 }
+
+// ------------------------------------------------------------------------------------------ batched eval renders
+// V eval-mode views of one scene in ONE call (render_reverse renders every training view, gc_pipeline.py:126-133): the
+// host loop over fused project+SH -> binning -> fused rgb+depth composite runs here instead of in the interpreter
+// (~13 launches per view; from Python the loop was launch-overhead-bound at 0.36 ms per view, above the GPU time).
+// The views are stream-ordered, so they share one set of intermediates; every view has its own outputs and its own
+// (M, overflow) pair.  Nothing synchronises.
+namespace {
+inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace
+
+extern "C" size_t gcb_bin_gaussians_workspace_bytes(int N, long long isect_capacity, int tile_bx, int tile_by);
+extern "C" int gcb_bin_gaussians(const float* xys, const float* depths, const int32_t* radii, const int32_t* num_tiles_hit,
+                                 int N, int tile_bx, int tile_by, long long isect_capacity, int32_t* gaussian_ids,
+                                 int32_t* tile_bins, int32_t* isect_count, int64_t* isect_keys, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
+extern "C" size_t gcb_render_eval_batch_workspace_bytes(int N, long long isect_capacity, int img_h, int img_w) {
+    if (N <= 0 || isect_capacity <= 0 || img_h <= 0 || img_w <= 0) return 0;
+    const int tbx = gcb_cdiv(img_w, BLOCK), tby = gcb_cdiv(img_h, BLOCK);
+    return a256((size_t)N * 8) + 3 * a256((size_t)N * 4) + a256((size_t)N * 12) + a256((size_t)N * 16) + a256((size_t)N * 4) +
+           a256((size_t)isect_capacity * 4) + a256((size_t)tbx * tby * 8) +
+           gcb_bin_gaussians_workspace_bytes(N, isect_capacity, tbx, tby);
+}
+
+extern "C" int gcb_render_eval_batch(const float* means3d, const float* log_scales, const float* quats,
+                                     const float* features_dc, const float* features_rest, const float* opacity_logits,
+                                     int N, int sh_degree, int V, const float* h_viewmats, const float* h_projmats,
+                                     const float* h_cam_origins, const float* h_intrinsics, int img_h, int img_w,
+                                     const float* d_background3, long long isect_capacity, float* out_rgb, float* out_depth,
+                                     float* out_alpha, int32_t* isect_counts, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    GCB_CHECK_ARG(h_viewmats && h_projmats && h_cam_origins && h_intrinsics && d_background3, "null camera / background");
+    GCB_CHECK_ARG(out_rgb && out_depth && out_alpha && isect_counts && workspace, "null output / workspace");
+    GCB_CHECK_ARG(V >= 0 && N > 0, "bad V=%d / N=%d", V, N);
+    const size_t need = gcb_render_eval_batch_workspace_bytes(N, isect_capacity, img_h, img_w);
+    if (workspace_bytes < need || need == 0) {
+        gcb_set_error("render batch workspace too small: %zu < %zu", workspace_bytes, need);
+        return GCB_ERR_WORKSPACE;
+    }
+    const int tbx = gcb_cdiv(img_w, BLOCK), tby = gcb_cdiv(img_h, BLOCK);
+    char* w = (char*)workspace;
+    auto take = [&](size_t bytes) {
+        char* p = w;
+        w += a256(bytes);
+        return p;
+    };
+    float* xys = (float*)take((size_t)N * 8);
+    float* depths = (float*)take((size_t)N * 4);
+    int32_t* radii = (int32_t*)take((size_t)N * 4);
+    int32_t* nth = (int32_t*)take((size_t)N * 4);
+    float* conics = (float*)take((size_t)N * 12);
+    float* rgbd = (float*)take((size_t)N * 16);
+    float* opac = (float*)take((size_t)N * 4);
+    int32_t* gids = (int32_t*)take((size_t)isect_capacity * 4);
+    int32_t* bins = (int32_t*)take((size_t)tbx * tby * 8);
+    const size_t bin_bytes = gcb_bin_gaussians_workspace_bytes(N, isect_capacity, tbx, tby);
+    const size_t px = (size_t)img_h * img_w;
+    for (int v = 0; v < V; ++v) {
+        const float* in = h_intrinsics + 4 * v;
+        int rc = gcb_project_sh_fused_fwd(means3d, log_scales, quats, features_dc, features_rest, opacity_logits,
+                                          h_viewmats + 16 * v, h_projmats + 16 * v, h_cam_origins + 3 * v, in[0], in[1], in[2],
+                                          in[3], img_h, img_w, tbx, tby, sh_degree, N, xys, depths, radii, conics, nth, rgbd,
+                                          opac, stream);
+        if (rc != GCB_OK) return rc;
+        rc = gcb_bin_gaussians(xys, depths, radii, nth, N, tbx, tby, isect_capacity, gids, bins, isect_counts + 2 * v, nullptr,
+                               w, bin_bytes, stream);
+        if (rc != GCB_OK) return rc;
+        rc = gcb_rasterize_rgbd_fwd(xys, conics, rgbd, opac, gids, bins, radii, img_h, img_w, d_background3,
+                                    out_rgb + 3 * px * v, out_depth + px * v, out_alpha + px * v, stream);
+        if (rc != GCB_OK) return rc;
+    }
+    return GCB_OK;
+}

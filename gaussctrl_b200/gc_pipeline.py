@@ -254,13 +254,19 @@ class GaussCtrlPipeline(VanillaPipeline):
         The caller runs `gsplat_ops.check_deferred_overflow()` afterwards."""
         from . import gsplat_ops
         model = self.model
+        streams = None
+        if self.device_.type == "cuda" and self.raster_streams > 1:
+            if getattr(self, "_raster_streams", None) is None:
+                self._raster_streams = [torch.cuda.Stream(self.device_) for _ in range(self.raster_streams)]
+            streams = self._raster_streams
+        if hasattr(model, "get_outputs_for_cameras"):
+            # one batched call per stream (gcb_render_eval_batch): the per-view host loop runs in C
+            return model.get_outputs_for_cameras([self._camera_at(ci) for ci in view_ids], streams=streams)
         model.defer_isect_check = True
         try:
-            if self.device_.type == "cuda" and self.raster_streams > 1:
-                if getattr(self, "_raster_streams", None) is None:
-                    self._raster_streams = [torch.cuda.Stream(self.device_) for _ in range(self.raster_streams)]
+            if streams is not None:
                 return gsplat_ops.render_views_multistream(
-                    lambda ci: model.get_outputs_for_camera(self._camera_at(ci)), list(view_ids), self._raster_streams)
+                    lambda ci: model.get_outputs_for_camera(self._camera_at(ci)), list(view_ids), streams)
             return [model.get_outputs_for_camera(self._camera_at(ci)) for ci in view_ids]
         finally:
             model.defer_isect_check = False

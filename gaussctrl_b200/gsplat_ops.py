@@ -125,14 +125,32 @@ def check_deferred_overflow() -> None:
     pend, PENDING_OVERFLOW = PENDING_OVERFLOW, []
     if not pend:
         return
-    counts = torch.stack([c for c, _ in pend]).cpu()
-    LAST_M[0] = int(counts[-1, 0])
-    bad = [(int(counts[i, 0]), pend[i][1]) for i in range(len(pend)) if int(counts[i, 1])]
-    if bad:
-        for m, key in bad:
-            _BinBuffers.get(*key, min_cap=m)
-        raise IsectOverflow(f"{len(bad)} render(s) exceeded the intersection capacity (largest M = {max(m for m, _ in bad)});"
-                            f" capacity grown - render again")
+    torch.cuda.synchronize()
+    worst = 0
+    n_bad = 0
+    for counts, key in pend:
+        c = counts.reshape(-1, 2).cpu()
+        LAST_M[0] = int(c[-1, 0])
+        bad = c[c[:, 1] != 0]
+        if bad.numel():
+            m = int(bad[:, 0].max())
+            n_bad += bad.shape[0]
+            worst = max(worst, m)
+            _grow_capacity(key, m)
+    if n_bad:
+        raise IsectOverflow(f"{n_bad} render(s) exceeded the intersection capacity (largest M = {worst}); capacity grown - "
+                            f"render again")
+
+
+def _grow_capacity(key, m: int) -> None:
+    """key = (N, tbx, tby, dev) of a per-view binning or ("batch", N, H, W, dev) of a batched render."""
+    if key and key[0] == "batch":
+        _, N, H, W, dev = key
+        for k in [k for k in _BatchBuffers.cache if k[0] == str(dev) and k[2:] == (N, H, W)]:
+            del _BatchBuffers.cache[k]
+        _BatchBuffers.min_cap = max(getattr(_BatchBuffers, "min_cap", 0), m)
+    else:
+        _BinBuffers.get(*key, min_cap=m)
 
 
 class IsectOverflow(RuntimeError):
@@ -322,6 +340,74 @@ def render_eval_fused(params, viewmat, projmat, cam_origin, fx, fy, cx, cy, img_
     if not defer_check:
         check_deferred_overflow()
     return rgb, depth, alpha, xys, radii
+
+
+class _BatchBuffers:
+    """Per-(device, stream, N, H, W) workspace of gcb_render_eval_batch, sized for a sticky intersection capacity."""
+    cache: dict = {}
+
+    @classmethod
+    def get(cls, N: int, H: int, W: int, dev, min_cap: int = 0):
+        key = (str(dev), torch.cuda.current_stream().cuda_stream, N, H, W)
+        ent = cls.cache.get(key)
+        if ent is None or ent[0] < min_cap:
+            cap = max(min_cap, 1 << 16, min(8 * N, (1 << 30) - 1)) if ent is None else max(min_cap, 2 * ent[0])
+            cap = min(cap, (1 << 30) - 1)
+            nb = lib.gcb_render_eval_batch_workspace_bytes(N, cap, H, W)
+            ent = (cap, torch.empty((nb,), dtype=torch.uint8, device=dev))
+            if len(cls.cache) > 16:
+                cls.cache.clear()
+            cls.cache[key] = ent
+        return ent
+
+
+def render_eval_batch(params, viewmats, projmats, cam_origins, intrinsics, img_height, img_width, sh_degree, background,
+                      streams=None):
+    """Eval renders of V views in one C-ABI call per stream (gcb_render_eval_batch): viewmats / projmats [V,4,4] (projmat =
+    proj @ view), cam_origins [V,3], intrinsics [V,4] = (fx, fy, cx, cy) - host tensors.  The views are split into
+    len(streams) contiguous chunks that render concurrently.  No host synchronisation; the capacity check is deferred
+    (check_deferred_overflow()).  -> rgb [V,H,W,3], depth [V,H,W,1], alpha [V,H,W,1]."""
+    means = _f32(params["means"])
+    N, dev = means.shape[0], means.device
+    H, W = int(img_height), int(img_width)
+    V = int(viewmats.shape[0])
+    tens = [_f32(params[k]) for k in ("scales", "quats", "features_dc")]
+    rest = params.get("features_rest")
+    rest = None if rest is None else _f32(rest)
+    opl = _f32(params["opacities"]).reshape(-1)
+    rgb = torch.empty((V, H, W, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((V, H, W, 1), dtype=torch.float32, device=dev)
+    alpha = torch.empty((V, H, W, 1), dtype=torch.float32, device=dev)
+    counts = torch.zeros((V, 2), dtype=torch.int32, device=dev)
+    bg3 = background.detach().to(dev, torch.float32).reshape(3).contiguous()
+    vm = viewmats.detach().to("cpu", torch.float32).contiguous().numpy()
+    pm = projmats.detach().to("cpu", torch.float32).contiguous().numpy()
+    org = cam_origins.detach().to("cpu", torch.float32).contiguous().numpy()
+    intr = intrinsics.detach().to("cpu", torch.float32).contiguous().numpy()
+    fp = ctypes.POINTER(ctypes.c_float)
+    cur = torch.cuda.current_stream()
+    lanes = list(streams) if streams else [cur]
+    per = -(-V // len(lanes)) if V else 0
+    px = H * W
+    for li, st in enumerate(lanes):
+        v0, v1 = li * per, min(V, (li + 1) * per)
+        if v0 >= v1:
+            break
+        if st is not cur:
+            st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            cap, ws = _BatchBuffers.get(N, H, W, dev, getattr(_BatchBuffers, "min_cap", 0))
+            check(lib.gcb_render_eval_batch(
+                _p(means), _p(tens[0]), _p(tens[1]), _p(tens[2]), _p(rest), _p(opl), N, int(sh_degree), v1 - v0,
+                vm[v0:v1].ctypes.data_as(fp), pm[v0:v1].ctypes.data_as(fp), org[v0:v1].ctypes.data_as(fp),
+                intr[v0:v1].ctypes.data_as(fp), H, W, _p(bg3), cap, _p(rgb, v0 * px * 3), _p(depth, v0 * px),
+                _p(alpha, v0 * px), _p(counts, 2 * v0), _p(ws), ws.numel(), _stream()))
+        ops.LAUNCHES[0] += 13 * (v1 - v0)
+    for st in lanes:
+        if st is not cur:
+            cur.wait_stream(st)
+    PENDING_OVERFLOW.append((counts, ("batch", N, H, W, dev)))
+    return rgb, depth, alpha
 
 
 def rasterize_rgbd(xys, depths, radii, conics, num_tiles_hit, rgbs, opacity, img_height, img_width, background):

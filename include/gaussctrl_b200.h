@@ -203,6 +203,20 @@ int gcb_rasterize_rgbd_fwd(const float* xys, const float* conics, const float* r
                            int img_w, const float* d_background3, float* out_rgb, float* out_depth, float* out_alpha,
                            void* stream);
 
+/* V eval-mode renders of one scene in one call - the loop of render_reverse over the training views
+ * (gc_pipeline.py:126-133 -> gc_model.py:57-206 per view): for each view fused project+SH, binning, fused rgb+depth
+ * composite, stream-ordered on `stream`, sharing one set of intermediates in `workspace`.  Host arrays: h_viewmats /
+ * h_projmats [V,16] row-major 4x4, h_cam_origins [V,3], h_intrinsics [V,4] = (fx, fy, cx, cy).  Outputs: out_rgb
+ * [V,H,W,3], out_depth [V,H,W], out_alpha [V,H,W]; isect_counts device int32 [V,2] = (M, overflow) per view (see
+ * gcb_bin_gaussians).  Never synchronises. */
+size_t gcb_render_eval_batch_workspace_bytes(int N, long long isect_capacity, int img_h, int img_w);
+int gcb_render_eval_batch(const float* means3d, const float* log_scales, const float* quats, const float* features_dc,
+                          const float* features_rest, const float* opacity_logits, int N, int sh_degree, int V,
+                          const float* h_viewmats, const float* h_projmats, const float* h_cam_origins,
+                          const float* h_intrinsics, int img_h, int img_w, const float* d_background3,
+                          long long isect_capacity, float* out_rgb, float* out_depth, float* out_alpha,
+                          int32_t* isect_counts, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- reference-K/V exchange over NVLink peer memory (the one collective of the path; replaces the
  *      per-layer `ncclAllGather` a multi-GPU port of gc_pipeline.py:206-219 would issue).  One process per GPU; the
  *      host side exchanges the 64-byte IPC handles once (e.g. torch.distributed.all_gather_object).  All calls enqueue

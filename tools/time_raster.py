@@ -51,10 +51,30 @@ def main():
         res[name] = {"gpu_ms_per_view": e0.elapsed_time(e1) / V, "wall_ms_per_view": (time.perf_counter() - t0) * 1e3 / V}
     M = go.LAST_M[0]
     byts = 244.0 * n + 48.0 * n + 152.0 * M + 5.2e6
+    # batched C-side loop (gcb_render_eval_batch), what GaussCtrlPipeline.render_views uses
+    from gaussctrl_b200.gc_model import projection_matrix, viewmat_from_c2w
+    import math
+    W = H = 512
+    vms = [viewmat_from_c2w(c) for c in c2ws]
+    pm = projection_matrix(0.001, 1000, 2 * math.atan(W / (2 * intr[0])), 2 * math.atan(H / (2 * intr[1])))
+    pms = torch.stack([pm @ v for v in vms])
+    orgs = torch.stack([c[:3, 3] for c in c2ws])
+    it = torch.tensor([list(intr)] * V)
+    for rep in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        with torch.no_grad():
+            go.render_eval_batch(P, torch.stack(vms), pms, orgs, it, H, W, 3, bg, streams=streams)
+        e1.record()
+        torch.cuda.synchronize()
+        go.check_deferred_overflow()
+        res["batched"] = {"gpu_ms_per_view": e0.elapsed_time(e1) / V, "wall_ms_per_view": (time.perf_counter() - t0) * 1e3 / V}
     res["streams"] = n_streams
     res["intersections_last_view"] = M
     res["algorithmic_bytes"] = byts
     res["achieved_gbs_pipelined"] = byts / (res["pipelined"]["gpu_ms_per_view"] / 1e3) / 1e9
+    res["achieved_gbs_batched"] = byts / (res["batched"]["gpu_ms_per_view"] / 1e3) / 1e9
     print(json.dumps(res))
 
 
