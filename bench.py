@@ -483,6 +483,8 @@ def main():
             from gaussctrl_b200.gc_pipeline import crossview_ref_frames
             key = next(k for k in pipe.engine._steps if k[0] == "refs_once")
             view_step = pipe.engine._steps[key][2][0]
+            emb_e = pipe.prompt_encoder([pipe.negative_prompts, pipe.positive_prompt])
+            pipe.denoiser.set_prompts(torch.cat([emb_e[0:1], emb_e[1:2]], dim=0))   # stage A left its single prompt set
             ops.ATTN_EVENTS = []
             marks = []
             for _ in range(3):
