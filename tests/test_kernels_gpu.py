@@ -369,7 +369,9 @@ def test_batch_invariance(ops):
 
 
 @pytest.mark.parametrize("case", [(4, 512, 1.0, 40), (6, 1024, 1.0, 40), (4, 256, 1.0, 40), (4, 512, 6.0, 40),
-                                  (4, 256, 1.0, 80), (6, 1024, 1.0, 80), (4, 512, 6.0, 80)])
+                                  (4, 256, 1.0, 80), (6, 1024, 1.0, 80), (4, 512, 6.0, 80),
+                                  # N an ODD multiple of 128: the last CTA of a (row, head) owns one query slot only
+                                  (4, 128, 1.0, 40), (4, 384, 1.0, 40), (4, 384, 1.0, 80)])
 def test_tcgen05_attention(ops, case):
     """The tcgen05/TMEM multi-source kernel (head dims 40, 80) vs the oracle and vs the mma.sync kernel: literal layout
     (sources in the same buffer), cached-reference layout (second buffer), and the ControlNet weights (self weight 0).
