@@ -330,9 +330,10 @@ def main():
     g = torch.Generator().manual_seed(1)
     mine_a = list(range(rank, V, world))
     torch.cuda.synchronize()
-    outs = pipe.render_views(mine_a)      # warm-up: per-stream binning workspaces
-    _go.check_deferred_overflow()
-    del outs
+    for _ in range(2):                    # warm-up: per-stream workspaces, allocator pools of the side streams
+        outs = pipe.render_views(mine_a)
+        _go.check_deferred_overflow()
+        del outs
     torch.cuda.synchronize()
     e0, e1 = ev(), ev()
     e0.record()
@@ -587,9 +588,9 @@ def main():
                                      "frac_of_hbm_peak": raster_bytes / (raster_ms_per_view / 1e3) / 1e9 /
                                      float(json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6552.6))
                                      if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else None,
-                                     "note": "CUDA events around this rank's eval renders (GaussCtrlModel."
-                                             "get_outputs_for_camera) spread over 4 streams, no host synchronisation "
-                                             "inside; roofline bound = HBM"},
+                                     "note": "CUDA events around GaussCtrlPipeline.render_views of this rank's views "
+                                             "(GaussCtrlModel.get_outputs_for_cameras: one gcb_render_eval_batch call per "
+                                             "stream, 4 streams, no host synchronisation inside); roofline bound = HBM"},
                           "schedule": "refs_once (reference views denoised once per DDIM step, K/V recorded)",
                           "view_batch": args.view_batch, "breakdown": breakdown,
                           "render_reverse_ms": stage_a_ms, "finetune": finetune,

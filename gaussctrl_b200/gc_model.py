@@ -194,19 +194,18 @@ class GaussCtrlModel(SplatfactoModel):
             background = renderers.BACKGROUND_COLOR_OVERRIDE.to(self.device)
         else:
             background = self.background_color.to(self.device)
-        vms, pms, orgs, intr = [], [], [], []
-        for c in cams:
+
+        def camera(i):
+            c = cams[i]
             c2w = c.camera_to_worlds[0].detach().to("cpu", torch.float32)
             fx, fy, cx, cy = c.fx.item(), c.fy.item(), c.cx.item(), c.cy.item()
             vm = viewmat_from_c2w(c2w)
             pm = projection_matrix(0.001, 1000, 2 * math.atan(W / (2 * fx)), 2 * math.atan(H / (2 * fy)))
-            vms.append(vm)
-            pms.append(pm @ vm)
-            orgs.append(c2w[:3, 3])
-            intr.append(torch.tensor([fx, fy, cx, cy], dtype=torch.float32))
+            return vm, pm @ vm, c2w[:3, 3], (fx, fy, cx, cy)
+
+        camera.n_views = len(cams)
         params = {k: getattr(self, k) for k in ("means", "scales", "quats", "features_dc", "features_rest", "opacities")}
-        rgb, depth, alpha = gsplat_ops.render_eval_batch(params, torch.stack(vms), torch.stack(pms), torch.stack(orgs),
-                                                         torch.stack(intr), H, W, n, background, streams=streams)
+        rgb, depth, alpha = gsplat_ops.render_eval_batch(params, camera, H, W, n, background, streams=streams)
         self.last_size = (H, W)
         return [{"rgb": rgb[i], "depth": depth[i], "accumulation": alpha[i]} for i in range(len(cams))]
 

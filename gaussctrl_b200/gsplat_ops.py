@@ -361,16 +361,23 @@ class _BatchBuffers:
         return ent
 
 
-def render_eval_batch(params, viewmats, projmats, cam_origins, intrinsics, img_height, img_width, sh_degree, background,
-                      streams=None):
-    """Eval renders of V views in one C-ABI call per stream (gcb_render_eval_batch): viewmats / projmats [V,4,4] (projmat =
-    proj @ view), cam_origins [V,3], intrinsics [V,4] = (fx, fy, cx, cy) - host tensors.  The views are split into
-    len(streams) contiguous chunks that render concurrently.  No host synchronisation; the capacity check is deferred
-    (check_deferred_overflow()).  -> rgb [V,H,W,3], depth [V,H,W,1], alpha [V,H,W,1]."""
+def render_eval_batch(params, cameras, img_height, img_width, sh_degree, background, streams=None):
+    """Eval renders of V views in one C-ABI call per stream (gcb_render_eval_batch).  `cameras(i)` returns the host-side
+    camera of view i as (viewmat [4,4], projmat = proj @ view [4,4], cam_origin [3], (fx, fy, cx, cy)); `cameras` may also
+    be a tuple of four stacked tensors.  The views are split into len(streams) contiguous chunks that render concurrently;
+    a chunk's cameras are evaluated right before its launch, so the host-side matrix math of chunk k+1 overlaps the GPU
+    work of chunk k.  No host synchronisation; the capacity check is deferred (check_deferred_overflow()).
+    -> rgb [V,H,W,3], depth [V,H,W,1], alpha [V,H,W,1]."""
+    import numpy as np
     means = _f32(params["means"])
     N, dev = means.shape[0], means.device
     H, W = int(img_height), int(img_width)
-    V = int(viewmats.shape[0])
+    if callable(cameras):
+        cam_fn, V = cameras, int(getattr(cameras, "n_views"))
+    else:
+        vm_t, pm_t, org_t, intr_t = cameras
+        V = int(vm_t.shape[0])
+        cam_fn = lambda i: (vm_t[i], pm_t[i], org_t[i], intr_t[i])  # noqa: E731
     tens = [_f32(params[k]) for k in ("scales", "quats", "features_dc")]
     rest = params.get("features_rest")
     rest = None if rest is None else _f32(rest)
@@ -380,28 +387,30 @@ def render_eval_batch(params, viewmats, projmats, cam_origins, intrinsics, img_h
     alpha = torch.empty((V, H, W, 1), dtype=torch.float32, device=dev)
     counts = torch.zeros((V, 2), dtype=torch.int32, device=dev)
     bg3 = background.detach().to(dev, torch.float32).reshape(3).contiguous()
-    vm = viewmats.detach().to("cpu", torch.float32).contiguous().numpy()
-    pm = projmats.detach().to("cpu", torch.float32).contiguous().numpy()
-    org = cam_origins.detach().to("cpu", torch.float32).contiguous().numpy()
-    intr = intrinsics.detach().to("cpu", torch.float32).contiguous().numpy()
     fp = ctypes.POINTER(ctypes.c_float)
     cur = torch.cuda.current_stream()
     lanes = list(streams) if streams else [cur]
     per = -(-V // len(lanes)) if V else 0
     px = H * W
+    f32 = lambda t: np.ascontiguousarray(torch.as_tensor(t, dtype=torch.float32).detach().cpu().numpy(), dtype=np.float32)  # noqa: E731
     for li, st in enumerate(lanes):
         v0, v1 = li * per, min(V, (li + 1) * per)
         if v0 >= v1:
             break
+        cams = [cam_fn(i) for i in range(v0, v1)]
+        vm = np.stack([f32(c[0]).reshape(16) for c in cams])
+        pm = np.stack([f32(c[1]).reshape(16) for c in cams])
+        org = np.stack([f32(c[2]).reshape(3) for c in cams])
+        intr = np.stack([f32(c[3]).reshape(4) for c in cams])
         if st is not cur:
             st.wait_stream(cur)
         with torch.cuda.stream(st):
             cap, ws = _BatchBuffers.get(N, H, W, dev, getattr(_BatchBuffers, "min_cap", 0))
             check(lib.gcb_render_eval_batch(
                 _p(means), _p(tens[0]), _p(tens[1]), _p(tens[2]), _p(rest), _p(opl), N, int(sh_degree), v1 - v0,
-                vm[v0:v1].ctypes.data_as(fp), pm[v0:v1].ctypes.data_as(fp), org[v0:v1].ctypes.data_as(fp),
-                intr[v0:v1].ctypes.data_as(fp), H, W, _p(bg3), cap, _p(rgb, v0 * px * 3), _p(depth, v0 * px),
-                _p(alpha, v0 * px), _p(counts, 2 * v0), _p(ws), ws.numel(), _stream()))
+                vm.ctypes.data_as(fp), pm.ctypes.data_as(fp), org.ctypes.data_as(fp), intr.ctypes.data_as(fp), H, W, _p(bg3),
+                cap, _p(rgb, v0 * px * 3), _p(depth, v0 * px), _p(alpha, v0 * px), _p(counts, 2 * v0), _p(ws), ws.numel(),
+                _stream()))
         ops.LAUNCHES[0] += 13 * (v1 - v0)
     for st in lanes:
         if st is not cur:

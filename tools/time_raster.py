@@ -65,7 +65,7 @@ def main():
         t0 = time.perf_counter()
         e0.record()
         with torch.no_grad():
-            go.render_eval_batch(P, torch.stack(vms), pms, orgs, it, H, W, 3, bg, streams=streams)
+            go.render_eval_batch(P, (torch.stack(vms), pms, orgs, it), H, W, 3, bg, streams=streams)
         e1.record()
         torch.cuda.synchronize()
         go.check_deferred_overflow()
