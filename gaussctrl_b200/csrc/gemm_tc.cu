@@ -16,6 +16,8 @@
 #include "../../include/gaussctrl_b200.h"
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace {
 
 constexpr int BM = 128;
@@ -59,9 +61,24 @@ __device__ __forceinline__ void stage_row_half(uint32_t buf, int lane, int half,
     }
 }
 
+// Fused GEMM + all-gather (sharded reference pass): besides its own output tensor the epilogue stores every
+// staged 32x64 tile into the SAME coordinates of up to 7 peers' arenas (TMA bulk stores over NVLink) - the transfer of
+// tile i overlaps the main loop / epilogue of tile i+1 instead of following the GEMM as a separate push kernel.
+constexpr int MAX_PEER_MAPS = 7;
+struct alignas(64) PeerMaps {
+    CUtensorMap m[MAX_PEER_MAPS];
+    __half* y[MAX_PEER_MAPS];   // the same tensors as raw pointers: a tile whose last 32-column chunk has no partner (BN = 160)
+    int n;                      // is stored per thread, and then to the peers as well
+};
+struct NoPeers {
+    int n;
+};
+
+template <bool PEER>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
-                                                      const __grid_constant__ CUtensorMap tmY, const GemmTcParams p) {
+                                                      const __grid_constant__ CUtensorMap tmY, const GemmTcParams p,
+                                                      const __grid_constant__ typename std::conditional<PEER, PeerMaps, NoPeers>::type pm) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -186,6 +203,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             __syncwarp();
             if (issuer) {
                 tma_store_2d(&tmY, stage_buf + (uint32_t)((n_pairs & 1) * 4096), col0, y_row0);
+                if constexpr (PEER) {
+                    for (int q_ = 0; q_ < pm.n; ++q_)
+                        tma_store_2d(&pm.m[q_], stage_buf + (uint32_t)((n_pairs & 1) * 4096), col0, y_row0);
+                }
                 tma_store_commit();
             }
             ++n_pairs;
@@ -249,14 +270,21 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                             stage_row_half(stage_buf + (uint32_t)((n_pairs & 1) * 4096), lane, c & 1, v);
                         } else {
                             uint4* op = reinterpret_cast<uint4*>(yp);
+                            uint4 o[4];
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                uint4 o;
-                                o.x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]);
-                                o.y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
-                                o.z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]);
-                                o.w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
-                                op[g] = o;
+                                o[g].x = pack_half2(v[g * 8 + 0], v[g * 8 + 1]);
+                                o[g].y = pack_half2(v[g * 8 + 2], v[g * 8 + 3]);
+                                o[g].z = pack_half2(v[g * 8 + 4], v[g * 8 + 5]);
+                                o[g].w = pack_half2(v[g * 8 + 6], v[g * 8 + 7]);
+                                op[g] = o[g];
+                            }
+                            if constexpr (PEER) {
+                                for (int q_ = 0; q_ < pm.n; ++q_) {
+                                    uint4* pq = reinterpret_cast<uint4*>(pm.y[q_] + m * p.ldy + n0);
+#pragma unroll
+                                    for (int g = 0; g < 4; ++g) pq[g] = o[g];
+                                }
                             }
                         }
                     } else {
@@ -355,7 +383,14 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 step(vb, gb, s + 1);
             }
         }
-        if (p.epi && issuer) tma_store_wait_read<0>();  // smem must outlive the bulk stores that read it
+        if constexpr (PEER) {
+            // the peers' copies (bulk stores and the per-thread stores of an unpaired chunk) must be complete and visible
+            // system-wide before the kernel that follows in the stream raises this rank's flag
+            if (p.epi && issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __threadfence_system();
+        } else {
+            if (p.epi && issuer) tma_store_wait_read<0>();  // smem must outlive the bulk stores that read it
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -427,9 +462,22 @@ int gcb_gemm_tc_supported(int B, int H, int W, int Cin, int Cout, int ksize, int
     return 1;
 }
 
+int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
+                             const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
+                             int direct_epilogue, void* const* peer_y, int n_peer, cudaStream_t stream);
+
 int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
                        const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
                        int direct_epilogue, cudaStream_t stream) {
+    return gcb_gemm_tc_launch_peers(x, w, bias, rowvec, rowvec_ld, residual, y, B, H, W, Cin, Cout, ksize, act,
+                                    direct_epilogue, nullptr, 0, stream);
+}
+
+// peer_y[0..n_peer): the same output tensor in the peers' memory (every staged tile is stored there as well).  Needs the
+// TMA-store epilogue with complete 64-column groups: Cout % 64 == 0, no GEGLU, no direct epilogue.
+int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
+                             const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
+                             int direct_epilogue, void* const* peer_y, int n_peer, cudaStream_t stream) {
     GemmTcParams p;
     memset(&p, 0, sizeof(p));
     const long long M = (long long)B * H * W;
@@ -501,10 +549,31 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
     }
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     static unsigned long long configured = 0;   // one bit per device ordinal
-    if (gcb_first_use_on_device(configured))
-        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    if (gcb_first_use_on_device(configured)) {
+        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    }
     dim3 grid(gcb_cdiv(Cout, p.BN), gcb_cdiv(M, BM));
-    gemm_tc_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p);
+    if (n_peer > 0) {
+        GCB_CHECK_ARG(n_peer <= MAX_PEER_MAPS && peer_y, "at most %d peer outputs", MAX_PEER_MAPS);
+        GCB_CHECK_ARG(p.epi && act != GCB_ACT_GEGLU && Cout % 64 == 0,
+                      "fused all-gather needs the TMA-store epilogue with full 64-column groups (Cout=%d)", Cout);
+        PeerMaps pm;
+        memset(&pm, 0, sizeof(pm));
+        pm.n = n_peer;
+        const uint64_t dims[2] = {(uint64_t)p.ldy, (uint64_t)M};
+        const uint64_t strides[1] = {(uint64_t)p.ldy * 2};
+        const uint32_t box[2] = {64, 32};
+        for (int q = 0; q < n_peer; ++q) {
+            rc = gcb_encode_tma(&pm.m[q], peer_y[q], 2, dims, strides, box, 1);
+            if (rc != GCB_OK) return rc;
+            pm.y[q] = (__half*)peer_y[q];
+        }
+        gemm_tc_kernel<true><<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p, pm);
+    } else {
+        NoPeers np{0};
+        gemm_tc_kernel<false><<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p, np);
+    }
     GCB_LAUNCH_CHECK();
     return GCB_OK;
 }

@@ -23,6 +23,10 @@ from . import ops
 from ._lib import GCB_ACT_GEGLU, GCB_ACT_NONE, GCB_ACT_SILU, GCB_GEMM_TCGEN05
 from .sd15_spec import skip_channels
 
+import os as _os
+
+_FUSED_GATHER = _os.environ.get("GCB_FUSED_GATHER", "1") != "0"   # A/B switch: projection GEMM + exchange as one kernel
+
 
 @dataclass
 class AttnPlan:
@@ -279,15 +283,29 @@ class SD15Denoiser:
             ld, vstride = 2 * C + heads * 48, 48
         else:
             wqkv, _ = net.cat_lin([blk + ".attn1.to_q", blk + ".attn1.to_k", blk + ".attn1.to_v"])
-            qkv = ops.linear(n1, wqkv)  # [B,N,3C]
+            qkv = None
             ld, vstride = 3 * C, d
         layer = f"{net_id}:{blk}.attn1"
+        kv2 = None
         if plan.gather is not None:
-            # sharded reference pass (parallel.py): all-gather the rows' q|k|v so every reference row sees all references
-            kv2 = plan.gather(layer, qkv)
+            # sharded reference pass (parallel.py): every rank needs the q|k|v rows of ALL reference rows
+            fused = None
+            if qkv is None and _FUSED_GATHER and hasattr(plan.gather, "linear_gather"):
+                # one kernel: the GEMM's epilogue stores every output tile into all ranks' K/V buffers over NVLink
+                # (gcb_linear_allgather_fwd); the local rows are read back out of the gathered buffer
+                fused = plan.gather.linear_gather(layer, n1, wqkv)
+            if fused is not None:
+                kv2, qkv = fused
+                ops.LAUNCHES[0] += 2
+            else:
+                if qkv is None:
+                    qkv = ops.linear(n1, wqkv)  # [B,N,3C]
+                kv2 = plan.gather(layer, qkv)   # GEMM, then push + flag kernels (or NCCL)
             if plan.record_kv is not None:
                 plan.record_kv[layer] = kv2
         else:
+            if qkv is None:
+                qkv = ops.linear(n1, wqkv)  # [B,N,3C]
             if plan.record_kv is not None:
                 plan.record_kv[layer] = qkv
             kv2 = plan.ref_kv[layer] if plan.ref_kv is not None else None

@@ -154,6 +154,10 @@ class _ParityGather:
     def check(self) -> None:
         self.inner.check()
 
+    def linear_gather(self, layer: str, x: torch.Tensor, w: torch.Tensor, bias=None):
+        fn = getattr(self.inner, "linear_gather", None)
+        return None if fn is None else fn(layer + self.tag, x, w, bias)
+
 
 class EditEngine:
     def __init__(self, denoiser: SD15Denoiser, tables: Optional[DDIMTables] = None, use_graphs: bool = True,

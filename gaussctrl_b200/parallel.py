@@ -181,11 +181,15 @@ class PeerKVAllGather:
         self.bytes = 0
         dist.barrier(group=group)
 
-    def _region(self, layer: str, local: torch.Tensor):
+    def _region(self, layer: str, local):
+        """`local`: this rank's block (a tensor, or just its shape): [rows, ...] fp16."""
+        shape_l = tuple(local.shape) if isinstance(local, torch.Tensor) else tuple(local)
         ent = self.regions.get(layer)
-        per_bytes = local.numel() * local.element_size()
-        if ent is None or ent[3] != per_bytes or tuple(ent[2].shape[1:]) != tuple(local.shape[1:]):
-            if local.dtype != torch.float16:
+        per_bytes = 2
+        for d_ in shape_l:
+            per_bytes *= int(d_)
+        if ent is None or ent[3] != per_bytes or tuple(ent[2].shape[1:]) != shape_l[1:]:
+            if isinstance(local, torch.Tensor) and local.dtype != torch.float16:
                 raise TypeError("PeerKVAllGather carries fp16 tensors")
             if per_bytes % 16:
                 raise ValueError(f"{layer}: {per_bytes} bytes per rank is not a multiple of 16")
@@ -200,7 +204,7 @@ class PeerKVAllGather:
                 slot = 1 + len(self.regions)       # slot 0 is the pass barrier
             if slot >= 128:
                 raise RuntimeError("more than 127 gathered buffers")
-            shape = (self.world * local.shape[0],) + tuple(local.shape[1:])
+            shape = (self.world * shape_l[0],) + shape_l[1:]
             view = torch.as_tensor(_ArenaView(self.base + off, shape, "<f2"), device=self.dev)
             self.cursor = off + total
             ent = (off, slot, view, per_bytes)
@@ -217,6 +221,21 @@ class PeerKVAllGather:
                                                    torch.cuda.current_stream().cuda_stream))
         self.bytes += per_bytes * self.world
         return view
+
+    def linear_gather(self, layer: str, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        """Projection + exchange in ONE kernel (gcb_linear_allgather_fwd): y = x w^T for this rank's rows x [per, N, Cin],
+        every output tile stored by the GEMM epilogue into all ranks' arenas.  -> (gathered [world*per, N, Cout], the
+        local rows' view into it).  Falls back to GEMM + push (None) when the shape is outside the fused kernel's limits."""
+        if self.world > 8 or w.shape[0] % 64 != 0 or x.dtype != torch.float16 or not x.is_contiguous():
+            return None
+        per, N, Cin = x.shape
+        Cout = w.shape[0]
+        off, slot, view, per_bytes = self._region(layer, (per, N, Cout))
+        self._check(self._lib.gcb_linear_allgather_fwd(self.handle, x.data_ptr(), w.data_ptr(),
+                                                       None if bias is None else bias.data_ptr(), per * N, Cin, Cout, off,
+                                                       slot, torch.cuda.current_stream().cuda_stream))
+        self.bytes += per_bytes * self.world
+        return view, view[self.rank * per:(self.rank + 1) * per]
 
     def check(self) -> None:
         """Synchronous: raises if any wait of this rank timed out."""

@@ -236,6 +236,12 @@ int gcb_handle_ipc_open(gcb_handle_t* handle, int peer, const unsigned char* in6
  * names the flag set; use one slot per concurrently live buffer. */
 int gcb_allgather_ref_kv(gcb_handle_t* handle, size_t arena_offset, const void* local_src, size_t bytes_per_rank, int slot,
                          void* stream);
+/* The K/V projection and its exchange as ONE kernel: y = x w^T (+ bias), x [M,Cin] = this rank's rows, w [Cout,Cin]
+ * (Cout % 64 == 0); the tcgen05 GEMM's epilogue stores every output tile into all ranks' arenas (TMA bulk stores over
+ * NVLink to the peers) at arena_offset + rank * M * Cout * 2 - the layout gcb_allgather_ref_kv produces - and the flag
+ * exchange follows.  At most 8 ranks. */
+int gcb_linear_allgather_fwd(gcb_handle_t* handle, const void* x, const void* w, const void* bias, int M, int Cin, int Cout,
+                             size_t arena_offset, int slot, void* stream);
 /* Cross-rank barrier in stream order (guards the reuse of gathered blocks that peers still read). */
 int gcb_peer_barrier(gcb_handle_t* handle, int slot, void* stream);
 /* Synchronous: *out != 0 when a wait timed out (a peer never signalled); the gathered data is then invalid. */

@@ -80,6 +80,20 @@ def test_peer_gather_object_world1():
         torch.cuda.synchronize()
         assert ga2.data_ptr() == ga.data_ptr() and torch.equal(ga2, a2)     # stable address per layer: graphs can read it
         gather.check()
+        # projection + exchange as one kernel (gcb_linear_allgather_fwd): equals the plain GEMM, bit for bit
+        from gaussctrl_b200 import ops
+        x = torch.randn((2, 256, 320), device="cuda").half()
+        w = (torch.randn((960, 320), device="cuda") / 18).half()
+        full, local = gather.linear_gather("layerC", x, w)
+        torch.cuda.synchronize()
+        want = ops.linear(x, w)
+        assert full.shape == (2, 256, 960) and torch.equal(full, want) and torch.equal(local, want)
+        x2 = torch.randn((1, 64, 1280), device="cuda").half()          # M = 64 < one 128-row tile
+        w2 = (torch.randn((3840, 1280), device="cuda") / 36).half()
+        full2, _ = gather.linear_gather("layerD", x2, w2)
+        torch.cuda.synchronize()
+        assert torch.equal(full2, ops.linear(x2, w2))
+        assert gather.linear_gather("layerE", x, w[:100].contiguous()) is None   # Cout % 64 != 0: caller falls back
         with pytest.raises(MemoryError):
             gather("too_big", torch.zeros((64, 4096, 960), device="cuda").half())
         gather.close()
