@@ -68,7 +68,7 @@ SIGNATURES = {
     "gcb_handle_ipc_export": (c_int, [_P, ctypes.c_char_p]),
     "gcb_handle_ipc_open": (c_int, [_P, c_int, ctypes.c_char_p]),
     "gcb_allgather_ref_kv": (c_int, [_P, c_size_t, _P, c_size_t, c_int, _P]),
-    "gcb_linear_allgather_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_size_t, c_int, _P]),
+    "gcb_linear_allgather_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_size_t, c_int, _P]),
     "gcb_peer_barrier": (c_int, [_P, c_int, _P]),
     "gcb_handle_error": (c_int, [_P, POINTER(c_int)]),
     "gcb_rasterize_bwd": (c_int, [_P] * 6 + [c_int, c_int, c_int, _FP] + [_P] * 8 + [_P]),

@@ -69,6 +69,7 @@ struct alignas(64) PeerMaps {
     CUtensorMap m[MAX_PEER_MAPS];
     __half* y[MAX_PEER_MAPS];   // the same tensors as raw pointers: a tile whose last 32-column chunk has no partner (BN = 160)
     int n;                      // is stored per thread, and then to the peers as well
+    int col_min;                // output columns below this stay local (the Q third of a fused q|k|v projection)
 };
 struct NoPeers {
     int n;
@@ -204,8 +205,9 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             if (issuer) {
                 tma_store_2d(&tmY, stage_buf + (uint32_t)((n_pairs & 1) * 4096), col0, y_row0);
                 if constexpr (PEER) {
-                    for (int q_ = 0; q_ < pm.n; ++q_)
-                        tma_store_2d(&pm.m[q_], stage_buf + (uint32_t)((n_pairs & 1) * 4096), col0, y_row0);
+                    if (col0 + 64 > pm.col_min)   // any column of the group at or above col_min
+                        for (int q_ = 0; q_ < pm.n; ++q_)
+                            tma_store_2d(&pm.m[q_], stage_buf + (uint32_t)((n_pairs & 1) * 4096), col0, y_row0);
                 }
                 tma_store_commit();
             }
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                                 op[g] = o[g];
                             }
                             if constexpr (PEER) {
-                                for (int q_ = 0; q_ < pm.n; ++q_) {
+                                for (int q_ = 0; q_ < (n0 + 32 > pm.col_min ? pm.n : 0); ++q_) {
                                     uint4* pq = reinterpret_cast<uint4*>(pm.y[q_] + m * p.ldy + n0);
 #pragma unroll
                                     for (int g = 0; g < 4; ++g) pq[g] = o[g];
@@ -464,20 +466,21 @@ int gcb_gemm_tc_supported(int B, int H, int W, int Cin, int Cout, int ksize, int
 
 int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
                              const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
-                             int direct_epilogue, void* const* peer_y, int n_peer, cudaStream_t stream);
+                             int direct_epilogue, void* const* peer_y, int n_peer, int peer_col_min, cudaStream_t stream);
 
 int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
                        const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
                        int direct_epilogue, cudaStream_t stream) {
     return gcb_gemm_tc_launch_peers(x, w, bias, rowvec, rowvec_ld, residual, y, B, H, W, Cin, Cout, ksize, act,
-                                    direct_epilogue, nullptr, 0, stream);
+                                    direct_epilogue, nullptr, 0, 0, stream);
 }
 
 // peer_y[0..n_peer): the same output tensor in the peers' memory (every staged tile is stored there as well).  Needs the
-// TMA-store epilogue with complete 64-column groups: Cout % 64 == 0, no GEGLU, no direct epilogue.
+// TMA-store epilogue with complete 64-column groups: Cout % 64 == 0, no GEGLU, no direct epilogue.  Only output columns
+// >= peer_col_min (a multiple of 64) travel to the peers.
 int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
                              const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
-                             int direct_epilogue, void* const* peer_y, int n_peer, cudaStream_t stream) {
+                             int direct_epilogue, void* const* peer_y, int n_peer, int peer_col_min, cudaStream_t stream) {
     GemmTcParams p;
     memset(&p, 0, sizeof(p));
     const long long M = (long long)B * H * W;
@@ -561,6 +564,8 @@ int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, con
         PeerMaps pm;
         memset(&pm, 0, sizeof(pm));
         pm.n = n_peer;
+        pm.col_min = peer_col_min;
+        GCB_CHECK_ARG(peer_col_min >= 0 && peer_col_min % 64 == 0, "peer_col_min must be a multiple of 64");
         const uint64_t dims[2] = {(uint64_t)p.ldy, (uint64_t)M};
         const uint64_t strides[1] = {(uint64_t)p.ldy * 2};
         const uint32_t box[2] = {64, 32};

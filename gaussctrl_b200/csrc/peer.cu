@@ -201,17 +201,19 @@ extern "C" int gcb_allgather_ref_kv(gcb_handle_t* h, size_t arena_offset, const 
 int gcb_gemm_tc_supported(int B, int H, int W, int Cin, int Cout, int ksize, int act);
 int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
                              const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
-                             int direct_epilogue, void* const* peer_y, int n_peer, cudaStream_t stream);
+                             int direct_epilogue, void* const* peer_y, int n_peer, int peer_col_min, cudaStream_t stream);
 
 // y = x w^T (+ bias) for this rank's M rows, written by the GEMM's own epilogue into EVERY rank's arena at
 // arena_offset + rank * M * Cout * 2 (the layout of gcb_allgather_ref_kv), then the flag exchange: one kernel computes and
 // transfers, tile by tile, instead of GEMM -> push kernel.
 extern "C" int gcb_linear_allgather_fwd(gcb_handle_t* h, const void* x, const void* w, const void* bias, int M, int Cin,
-                                        int Cout, size_t arena_offset, int slot, void* stream) {
+                                        int Cout, int peer_col_min, size_t arena_offset, int slot, void* stream) {
     GCB_CHECK_ARG(h && x && w, "null pointer");
     GCB_CHECK_ARG(slot >= 0 && slot < MAX_SLOTS, "slot %d out of range", slot);
     GCB_CHECK_ARG(M > 0 && Cin > 0 && Cout > 0 && Cout % 64 == 0, "bad GEMM shape M=%d Cin=%d Cout=%d (Cout %% 64 == 0)", M,
                   Cin, Cout);
+    GCB_CHECK_ARG(peer_col_min >= 0 && peer_col_min < Cout && peer_col_min % 64 == 0, "peer_col_min=%d (multiple of 64, < Cout)",
+                  peer_col_min);
     const size_t bytes_per_rank = (size_t)M * Cout * 2;
     GCB_CHECK_ARG(arena_offset % 128 == 0 && arena_offset >= gcb_handle_control_bytes() &&
                       arena_offset + bytes_per_rank * (size_t)h->world <= h->arena_bytes,
@@ -231,7 +233,7 @@ extern "C" int gcb_linear_allgather_fwd(gcb_handle_t* h, const void* x, const vo
         if (q != h->rank) peers[n++] = P.arena[q] + off;
     GCB_CHECK_ARG(n <= 7, "fused all-gather supports up to 8 ranks");
     rc = gcb_gemm_tc_launch_peers(x, w, bias, nullptr, 0, nullptr, P.arena[h->rank] + off, 1, 1, M, Cin, Cout, 1, GCB_ACT_NONE,
-                                  0, peers, n, (cudaStream_t)stream);
+                                  0, peers, n, peer_col_min, (cudaStream_t)stream);
     if (rc != GCB_OK) return rc;
     peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(P, h->world, h->rank, slot);
     GCB_LAUNCH_CHECK();

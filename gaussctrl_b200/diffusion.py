@@ -293,7 +293,7 @@ class SD15Denoiser:
             if qkv is None and _FUSED_GATHER and hasattr(plan.gather, "linear_gather"):
                 # one kernel: the GEMM's epilogue stores every output tile into all ranks' K/V buffers over NVLink
                 # (gcb_linear_allgather_fwd); the local rows are read back out of the gathered buffer
-                fused = plan.gather.linear_gather(layer, n1, wqkv)
+                fused = plan.gather.linear_gather(layer, n1, wqkv, None, C)   # the Q third (C columns) stays local
             if fused is not None:
                 kv2, qkv = fused
                 ops.LAUNCHES[0] += 2

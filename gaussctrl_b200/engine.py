@@ -154,9 +154,9 @@ class _ParityGather:
     def check(self) -> None:
         self.inner.check()
 
-    def linear_gather(self, layer: str, x: torch.Tensor, w: torch.Tensor, bias=None):
+    def linear_gather(self, layer: str, x: torch.Tensor, w: torch.Tensor, bias=None, local_cols: int = 0):
         fn = getattr(self.inner, "linear_gather", None)
-        return None if fn is None else fn(layer + self.tag, x, w, bias)
+        return None if fn is None else fn(layer + self.tag, x, w, bias, local_cols)
 
 
 class EditEngine:

@@ -222,18 +222,24 @@ class PeerKVAllGather:
         self.bytes += per_bytes * self.world
         return view
 
-    def linear_gather(self, layer: str, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    def linear_gather(self, layer: str, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                      local_cols: int = 0):
         """Projection + exchange in ONE kernel (gcb_linear_allgather_fwd): y = x w^T for this rank's rows x [per, N, Cin],
         every output tile stored by the GEMM epilogue into all ranks' arenas.  -> (gathered [world*per, N, Cout], the
-        local rows' view into it).  Falls back to GEMM + push (None) when the shape is outside the fused kernel's limits."""
+        local rows' view into it).  The first `local_cols` output columns (a multiple of 64) are NOT sent to the peers -
+        the Q third of a q|k|v projection is read by its own rank only; the peers' copies of those columns are undefined.
+        Falls back to GEMM + push (None) when the shape is outside the fused kernel's limits."""
         if self.world > 8 or w.shape[0] % 64 != 0 or x.dtype != torch.float16 or not x.is_contiguous():
             return None
+        if local_cols % 64:
+            local_cols = 0
         per, N, Cin = x.shape
         Cout = w.shape[0]
         off, slot, view, per_bytes = self._region(layer, (per, N, Cout))
         self._check(self._lib.gcb_linear_allgather_fwd(self.handle, x.data_ptr(), w.data_ptr(),
-                                                       None if bias is None else bias.data_ptr(), per * N, Cin, Cout, off,
-                                                       slot, torch.cuda.current_stream().cuda_stream))
+                                                       None if bias is None else bias.data_ptr(), per * N, Cin, Cout,
+                                                       int(local_cols), off, slot,
+                                                       torch.cuda.current_stream().cuda_stream))
         self.bytes += per_bytes * self.world
         return view, view[self.rank * per:(self.rank + 1) * per]
 

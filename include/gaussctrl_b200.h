@@ -239,9 +239,10 @@ int gcb_allgather_ref_kv(gcb_handle_t* handle, size_t arena_offset, const void* 
 /* The K/V projection and its exchange as ONE kernel: y = x w^T (+ bias), x [M,Cin] = this rank's rows, w [Cout,Cin]
  * (Cout % 64 == 0); the tcgen05 GEMM's epilogue stores every output tile into all ranks' arenas (TMA bulk stores over
  * NVLink to the peers) at arena_offset + rank * M * Cout * 2 - the layout gcb_allgather_ref_kv produces - and the flag
- * exchange follows.  At most 8 ranks. */
+ * exchange follows.  Only output columns >= peer_col_min (a multiple of 64) are sent to the peers: with w = [to_q;to_k;to_v]
+ * and peer_col_min = C the Q third stays local (only its own rank reads it).  At most 8 ranks. */
 int gcb_linear_allgather_fwd(gcb_handle_t* handle, const void* x, const void* w, const void* bias, int M, int Cin, int Cout,
-                             size_t arena_offset, int slot, void* stream);
+                             int peer_col_min, size_t arena_offset, int slot, void* stream);
 /* Cross-rank barrier in stream order (guards the reuse of gathered blocks that peers still read). */
 int gcb_peer_barrier(gcb_handle_t* handle, int slot, void* stream);
 /* Synchronous: *out != 0 when a wait timed out (a peer never signalled); the gathered data is then invalid. */

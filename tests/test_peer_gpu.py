@@ -94,6 +94,9 @@ def test_peer_gather_object_world1():
         torch.cuda.synchronize()
         assert torch.equal(full2, ops.linear(x2, w2))
         assert gather.linear_gather("layerE", x, w[:100].contiguous()) is None   # Cout % 64 != 0: caller falls back
+        full3, _ = gather.linear_gather("layerF", x, w, None, 320)               # world = 1: local_cols changes nothing locally
+        torch.cuda.synchronize()
+        assert torch.equal(full3, want)
         with pytest.raises(MemoryError):
             gather("too_big", torch.zeros((64, 4096, 960), device="cuda").half())
         gather.close()
