@@ -5,8 +5,10 @@ This package restates, in plain PyTorch / numpy on the CPU, the algorithm of the
 they call).  It is the *checker* for the CUDA product in `gaussctrl_b200/` and the CPU baseline of
 `bench.py`; it is never the thing shipped or measured as the product.
 
-Import policy: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
-legs may import anything from here.  Nothing under `gaussctrl_b200/` imports `oracle`.
+Import policy: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s baseline legs (`cpu_baseline`,
+`--impl reference`, and `extra.reference_gpu_eager` = these same modules run in eager fp16 on the GPU as the
+"reference GPU pipeline" denominator) may import anything from here - always as the checker or the baseline, never
+inside a timed product region.  Nothing under `gaussctrl_b200/` imports `oracle`.
 
 Parity pinning status:
   * `crossview_attn`  – PINNED: checked against outputs of the reference's own `gaussctrl/utils.py`
