@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("GCB_LIB_PATH") or os.path.join(HERE, "libgaussctrl_b2
 
 GCB_ACT_NONE, GCB_ACT_SILU, GCB_ACT_GEGLU = 0, 1, 2
 GCB_GEMM_TCGEN05, GCB_GEMM_MMA_SYNC, GCB_GEMM_TCGEN05_DIRECT = 0, 1, 2
+GCB_GEMM_TCGEN05_PERSISTENT, GCB_GEMM_TCGEN05_ONE_TILE = 3, 4
 GCB_ATTN_AUTO, GCB_ATTN_TCGEN05, GCB_ATTN_MMA_SYNC = 0, 1, 2
 
 _P = c_void_p

@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 int gcb_gemm_tc_supported(int B, int H, int W, int Cin, int Cout, int ksize, int act);
+void gcb_gemm_tc_set_schedule(int schedule);
 int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const void* rowvec, int rowvec_ld,
                        const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int act,
                        int direct_epilogue, cudaStream_t stream);
@@ -232,7 +233,10 @@ extern "C" int gcb_conv2d_nhwc_fwd(const void* x, const void* w, const void* bia
     GCB_CHECK_ARG((long long)B * H * W < (1ll << 31), "M too large");
     cudaStream_t st = (cudaStream_t)stream;
     if (const char* e = getenv("GCB_FORCE_GEMM_IMPL")) impl = atoi(e);
-    if (impl == GCB_GEMM_TCGEN05 || impl == GCB_GEMM_TCGEN05_DIRECT) {
+    if (impl == GCB_GEMM_TCGEN05 || impl == GCB_GEMM_TCGEN05_DIRECT || impl == GCB_GEMM_TCGEN05_PERSISTENT ||
+        impl == GCB_GEMM_TCGEN05_ONE_TILE) {
+        // schedule of the tcgen05 kernel: by shape unless an A/B tool forces one
+        gcb_gemm_tc_set_schedule(impl == GCB_GEMM_TCGEN05_PERSISTENT ? 1 : impl == GCB_GEMM_TCGEN05_ONE_TILE ? 0 : -1);
         if (!gcb_gemm_tc_supported(B, H, W, Cin, Cout, ksize, act)) {
             gcb_set_error("tcgen05 path does not support B=%d H=%d W=%d Cin=%d Cout=%d k=%d act=%d", B, H, W, Cin, Cout,
                           ksize, act);

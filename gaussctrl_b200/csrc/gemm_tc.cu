@@ -2,8 +2,15 @@
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (kind::f16) -> TMEM accumulator
 //   -> software-pipelined tcgen05.ld epilogue (bias / per-image vector / residual / SiLU / GEGLU) -> 32x64 fp16 tiles
 //   staged in the (by then free) operand ring -> cp.async.bulk.tensor store (TMA), clipped at the tensor bounds.
-// Two CTAs are resident per SM (<= 110 KB of ring each, <= 256 TMEM columns each, 167 registers x 192 threads), so the
-// epilogue of one tile overlaps the main loop of another.  Measured per layer shape: profiles/r1i_gemm_table.txt.
+// Two schedules share one kernel body (template parameter PERSIST):
+//   * one tile per CTA: two CTAs resident per SM (<= 110 KB of ring each, <= 256 TMEM columns each, 167 registers x 192
+//     threads), so the epilogue of one tile overlaps the main loop of another.  Per layer shape: profiles/r1i_gemm_table.txt.
+//   * persistent: one CTA per SM walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs across tile
+//     boundaries (the operands of tile i+1 are in flight while tile i is multiplied), TWO accumulators live in TMEM so
+//     the main loop of tile i+1 runs under the epilogue of tile i, and EIGHT epilogue warps (two per TMEM lane quarter,
+//     each draining half of the 64-column groups) write through their own staging buffers.  This is the schedule for the
+//     short-K layers (K = 320 .. 1280 at M = 98 304), where a one-tile CTA spends most of its life in setup, first-load
+//     latency and drain instead of in the tensor pipe.
 //
 // y[M, Cout] = act( im2col(x)[M, taps*Cin] * w[Cout, taps*Cin]^T + bias + rowvec[b] ) + residual
 //
@@ -11,8 +18,8 @@
 // consecutive output pixels = a (bw x bh x bb) pixel box; filter tap (kh,kw) is the SAME box shifted by
 // (kw-1, kh-1) – TMA's out-of-bounds zero fill implements the padding, so no im2col buffer ever exists.
 // B operand: w is [Cout, taps*Cin] (K contiguous) -> 2-D TMA box (64 x BN).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (each owns the 32 TMEM lanes (warp_id % 4) * 32 ...).
+// Warp roles (192 / 320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 (2..9 when persistent) = epilogue (each owns the 32 TMEM lanes (warp_id % 4) * 32 ...).
 #include "../../include/gaussctrl_b200.h"
 #include "common.cuh"
 
@@ -42,6 +49,9 @@ struct GemmTcParams {
     int ldy;
     int act;
     int epi;           // 0 = each thread stores its own row (64 B pieces); 1 = 32x64 tiles staged in smem + TMA store
+    int n_tiles, ntiles;      // tiles along N, tiles in total (tile index = m_tile * n_tiles + n_tile)
+    uint32_t stage_off;       // persistent: byte offset of the epilogue staging area behind the operand ring
+    int stage_bufs;           // persistent: staging buffers per epilogue warp (1 or 2)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == GCB_ACT_SILU ? silu_f(v) : v; }
@@ -75,33 +85,41 @@ struct NoPeers {
     int n;
 };
 
-template <bool PEER>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB,
-                                                      const __grid_constant__ CUtensorMap tmY, const GemmTcParams p,
-                                                      const __grid_constant__ typename std::conditional<PEER, PeerMaps, NoPeers>::type pm) {
+template <bool PEER, bool PERSIST>
+__global__ void __launch_bounds__(PERSIST ? 320 : 192, PERSIST ? 1 : 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, const GemmTcParams p,
+               const __grid_constant__ typename std::conditional<PEER, PeerMaps, NoPeers>::type pm) {
+    static_assert(!(PEER && PERSIST), "the fused all-gather epilogue runs on the one-tile schedule");
+    constexpr int NH = PERSIST ? 2 : 1;          // epilogue warps per TMEM lane quarter (column halves)
+    constexpr int NEPI = 4 * NH;                 // epilogue warps
+    constexpr int NACC = PERSIST ? 2 : 1;        // accumulators in TMEM
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ __align__(8) uint64_t acc_full_bar[NACC];    // MMA -> epilogue: accumulator complete
+    __shared__ __align__(8) uint64_t acc_empty_bar[NACC];   // epilogue -> MMA: accumulator drained (persistent only)
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_stage_bytes = (uint32_t)p.BN * BK * 2;
     const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    const int tile_step = PERSIST ? (int)gridDim.x : p.ntiles;   // one-tile schedule: the loops below run once
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(&tmem_full_bar), 1);
+        for (int a = 0; a < NACC; ++a) {
+            mbar_init(smem_u32(&acc_full_bar[a]), 1);
+            mbar_init(smem_u32(&acc_empty_bar[a]), NEPI);
+        }
         mbar_fence_init();
     }
     if (warp == 1) {
-        tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols);
+        tmem_alloc(smem_u32(&tmem_base_smem), p.tmem_cols * NACC);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -115,80 +133,102 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
         }
-        int b0 = 0, h0 = 0, w0 = 0;
-        if (p.mode == 1) {
-            if (p.HW >= BM) {
-                const int tiles_per_img = p.HW / BM;
-                b0 = m_tile / tiles_per_img;
-                const int r = m_tile % tiles_per_img;
-                if (p.W >= BM) {
-                    const int segs = p.W / BM;
-                    h0 = r / segs;
-                    w0 = (r % segs) * BM;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += tile_step) {
+            const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+            int b0 = 0, h0 = 0, w0 = 0;
+            if (p.mode == 1) {
+                if (p.HW >= BM) {
+                    const int tiles_per_img = p.HW / BM;
+                    b0 = m_tile / tiles_per_img;
+                    const int r = m_tile % tiles_per_img;
+                    if (p.W >= BM) {
+                        const int segs = p.W / BM;
+                        h0 = r / segs;
+                        w0 = (r % segs) * BM;
+                    } else {
+                        h0 = r * p.bh;
+                    }
                 } else {
-                    h0 = r * p.bh;
+                    b0 = m_tile * p.bb;
                 }
-            } else {
-                b0 = m_tile * p.bb;
             }
-        }
-        for (int kb = 0; kb < p.nkb; ++kb) {
-            const int s = kb % p.stages;
-            const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-            if (elect_one_sync()) {
-                const uint32_t fb = smem_u32(&full_bar[s]);
-                mbar_expect_tx(fb, stage_bytes);
-                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-                const uint32_t sb = sa + A_STAGE_BYTES;
-                if (p.mode == 0) {
-                    tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * BM);
-                } else {
-                    const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-                    const int kh = tap / 3, kw = tap - kh * 3;
-                    tma_load_4d(sa, &tmA, fb, cb * BK, w0 + kw - 1, h0 + kh - 1, b0);
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                if (elect_one_sync()) {
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, stage_bytes);
+                    const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    if (p.mode == 0) {
+                        tma_load_2d(sa, &tmA, fb, kb * BK, m_tile * BM);
+                    } else {
+                        const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        tma_load_4d(sa, &tmA, fb, cb * BK, w0 + kw - 1, h0 + kh - 1, b0);
+                    }
+                    tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * p.BN);
                 }
-                tma_load_2d(sb, &tmB, fb, kb * BK, n_tile * p.BN);
+                __syncwarp();
+                if (++s == p.stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer: whole warp waits, one elected lane issues tcgen05.mma / commit ----------------
-        for (int kb = 0; kb < p.nkb; ++kb) {
-            const int s = kb % p.stages;
-            const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-            mbar_wait(smem_u32(&full_bar[s]), ph);
-            tc_fence_after();
-            if (elect_one_sync()) {
-                const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-                const uint32_t sb = sa + A_STAGE_BYTES;
-                const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
-                const uint64_t bdesc = make_smem_desc(sb, 16, 1024, 2);
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // advance 16 halves = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-                    tc_mma_ss(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc,
-                              (uint32_t)((kb | k) != 0));
-                }
-                tc_commit(smem_u32(&empty_bar[s]));
-                if (kb == p.nkb - 1) tc_commit(smem_u32(&tmem_full_bar));
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;   // tiles done by this CTA
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += tile_step, ++it) {
+            const int acc = PERSIST ? (it & 1) : 0;
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.tmem_cols;
+            if (PERSIST) {
+                // the epilogue of the tile before last must have drained this accumulator (first two uses pass at once)
+                mbar_wait(smem_u32(&acc_empty_bar[acc]), (((uint32_t)it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
             }
-            __syncwarp();
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    const uint64_t adesc = make_smem_desc(sa, 16, 1024, 2);
+                    const uint64_t bdesc = make_smem_desc(sb, 16, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 halves = 32 B inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+                        tc_mma_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    }
+                    tc_commit(smem_u32(&empty_bar[s]));
+                    if (kb == p.nkb - 1) tc_commit(smem_u32(&acc_full_bar[acc]));
+                }
+                __syncwarp();
+                if (++s == p.stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
         }
     } else {
-        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+        // ---------------- epilogue: warps 2.., TMEM lane quarter = warp % 4 ----------------
         // Software-pipelined: the tcgen05.ld of the NEXT column chunk is in flight while the current chunk is
         // converted, so the TMEM read latency is exposed once per tile instead of once per chunk.
+        // Persistent schedule: warps 2..5 take the even 64-column groups of a tile, warps 6..9 the odd ones.
         const int q = warp & 3;
+        const int half = PERSIST ? ((warp - 2) >> 2) : 0;
         const int row = q * 32 + lane;
-        const long long m = (long long)m_tile * BM + row;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const bool row_ok = m < p.M;
-        const int img = (p.rowvec != nullptr && row_ok) ? (int)(m / p.HW) : 0;
         const bool issuer = elect_one_sync() != 0;            // the one lane that issues / waits on this warp's TMA stores
-        const uint32_t stage_buf = smem_base + (uint32_t)q * 8192u;
-        const int y_row0 = m_tile * BM + q * 32;
-        int n_pairs = 0;                                        // staged 64-column groups so far (buffer = n_pairs & 1)
+        // staging: one-tile schedule = the (by then free) operand ring, 2 x 4 KB per warp; persistent = own area
+        const uint32_t stage_buf = PERSIST ? smem_base + p.stage_off + (uint32_t)((warp - 2) * p.stage_bufs) * 4096u
+                                           : smem_base + (uint32_t)q * 8192u;
+        const int nbufs = PERSIST ? p.stage_bufs : 2;
+        int n_pairs = 0;                                        // staged 64-column groups so far
+        int cur_buf = 0;                                        // staging buffer of the current group
         auto add8 = [](float* v, const uint4& u) {
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -198,26 +238,48 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 v[t * 2 + 1] += f.y;
             }
         };
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += tile_step, ++it) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int acc = PERSIST ? (it & 1) : 0;
+        const uint32_t acc_par = PERSIST ? (((uint32_t)it >> 1) & 1u) : 0u;
+        const long long m = (long long)m_tile * BM + row;
+        const uint32_t taddr = tmem_base + (uint32_t)acc * p.tmem_cols + ((uint32_t)(q * 32) << 16);
+        const bool row_ok = m < p.M;
+        const int img = (p.rowvec != nullptr && row_ok) ? (int)(m / p.HW) : 0;
+        const int y_row0 = m_tile * BM + q * 32;
         // a 64-column group is complete in the staging buffer: one bulk store, then switch buffers
         auto flush_group = [&](int col0) {
             fence_proxy_async_smem();
             __syncwarp();
             if (issuer) {
-                tma_store_2d(&tmY, stage_buf + (uint32_t)((n_pairs & 1) * 4096), col0, y_row0);
+                tma_store_2d(&tmY, stage_buf + (uint32_t)(cur_buf * 4096), col0, y_row0);
                 if constexpr (PEER) {
                     if (col0 + 64 > pm.col_min)   // any column of the group at or above col_min
                         for (int q_ = 0; q_ < pm.n; ++q_)
-                            tma_store_2d(&pm.m[q_], stage_buf + (uint32_t)((n_pairs & 1) * 4096), col0, y_row0);
+                            tma_store_2d(&pm.m[q_], stage_buf + (uint32_t)(cur_buf * 4096), col0, y_row0);
                 }
                 tma_store_commit();
             }
             ++n_pairs;
+            cur_buf = (cur_buf + 1 == nbufs) ? 0 : cur_buf + 1;
         };
         // before the first write into a staging buffer: the bulk store that last used it must have read it
         auto acquire_buffer = [&]() {
-            if (n_pairs >= 2) {
-                if (issuer) tma_store_wait_read<1>();
+            if (n_pairs >= nbufs) {
+                if (issuer) {
+                    if (nbufs == 2) tma_store_wait_read<1>();
+                    else tma_store_wait_read<0>();
+                }
                 __syncwarp();
+            }
+        };
+        // the accumulator is in registers / stored: hand it back to the MMA issuer
+        auto release_acc = [&]() {
+            if (PERSIST) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty_bar[acc]));
             }
         };
         if (p.act != GCB_ACT_GEGLU) {
@@ -236,13 +298,14 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 }
             };
             bool pair_staged = false;
-            auto chunk = [&](const uint32_t (&r)[32], int c) {
+            // c = this chunk, c_next = the chunk this warp converts after it (>= nchunks: none)
+            auto chunk = [&](const uint32_t (&r)[32], int c, int c_next) {
                 const int n0 = ncol0 + c * 32;
                 if ((c & 1) == 0) {
                     pair_staged = p.epi && c + 1 < nchunks && n0 + 64 <= p.N;
                     if (pair_staged) acquire_buffer();
                 }
-                if (c + 1 < nchunks) load_res(c + 1, res_nxt);
+                if (c_next < nchunks) load_res(c_next, res_nxt);
                 const bool full = n0 + 32 <= p.N;
                 if ((row_ok || pair_staged) && n0 < p.N) {
                     float v[32];
@@ -269,7 +332,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                             for (int g = 0; g < 4; ++g) add8(v + g * 8, res_cur[g]);
                         }
                         if (pair_staged) {
-                            stage_row_half(stage_buf + (uint32_t)((n_pairs & 1) * 4096), lane, c & 1, v);
+                            stage_row_half(stage_buf + (uint32_t)(cur_buf * 4096), lane, c & 1, v);
                         } else {
                             uint4* op = reinterpret_cast<uint4*>(yp);
                             uint4 o[4];
@@ -308,23 +371,47 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 #pragma unroll
                 for (int g = 0; g < 4; ++g) res_cur[g] = res_nxt[g];
             };
-            load_res(0, res_cur);
-            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            int c = 2 * half;   // this warp's chunks: the pairs (c, c+1), c = 2*half, 2*half + 2*NH, ...
+            if (c < nchunks) load_res(c, res_cur);
+            mbar_wait(smem_u32(&acc_full_bar[acc]), acc_par);
             tc_fence_after();
-            if (p.epi) fence_proxy_async_smem();  // generic writes below follow the TMA (async proxy) fills of the ring
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32b_x32(taddr, ra);
-            for (int c = 0; c < nchunks; c += 2) {
-                tc_wait_ld();  // ra = chunk c
-                const bool has2 = c + 1 < nchunks;
-                if (has2) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), rb);
-                chunk(ra, c);
-                if (has2) {
-                    tc_wait_ld();  // rb = chunk c+1
-                    if (c + 2 < nchunks) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 2) * 32), ra);
-                    chunk(rb, c + 1);
+            if (!PERSIST && p.epi) fence_proxy_async_smem();  // generic writes below follow the TMA (async proxy) fills of the ring
+            if constexpr (PERSIST) {
+                // two epilogue warps per scheduler hide each other's TMEM-load latency: one chunk in registers at a time
+                // (the second register buffer of the one-tile schedule would not fit under the 168-register cap of a
+                // 320-thread CTA)
+                uint32_t ra[32];
+                while (c < nchunks) {
+                    const bool has2 = c + 1 < nchunks;
+                    const int c2 = c + 2 * NH;   // first chunk of this warp's next pair
+                    tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), ra);
+                    tc_wait_ld();
+                    if (!has2) release_acc();    // an unpaired last chunk (BN = 160): everything is in registers
+                    chunk(ra, c, has2 ? c + 1 : c2);
+                    if (has2) {
+                        tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), ra);
+                        tc_wait_ld();
+                        if (c2 >= nchunks) release_acc();   // every column this warp owns has left TMEM
+                        chunk(ra, c + 1, c2);
+                    }
+                    c = c2;
+                }
+            } else {
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(taddr, ra);
+                for (; c < nchunks; c += 2) {
+                    tc_wait_ld();  // ra = chunk c
+                    const bool has2 = c + 1 < nchunks;
+                    if (has2) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), rb);
+                    chunk(ra, c, c + 1);
+                    if (has2) {
+                        tc_wait_ld();  // rb = chunk c+1
+                        if (c + 2 < nchunks) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 2) * 32), ra);
+                        chunk(rb, c + 1, c + 2);
+                    }
                 }
             }
+            if (PERSIST && 2 * half >= nchunks) release_acc();   // nothing to drain in this tile (BN = 64)
         } else {
             // GEGLU: tile columns [0, BN/2) = value, [BN/2, BN) = gate; output width N/2.  Steps of 16 output columns
             // (16 value + 16 gate accumulators), double-buffered; four steps fill one 64-column staging group.
@@ -355,7 +442,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                                h3 = pack_half2(o[6], o[7]), h4 = pack_half2(o[8], o[9]), h5 = pack_half2(o[10], o[11]),
                                h6 = pack_half2(o[12], o[13]), h7 = pack_half2(o[14], o[15]);
                 if (p.epi) {
-                    const uint32_t buf = stage_buf + (uint32_t)((n_pairs & 1) * 4096) + (uint32_t)(lane * 128);
+                    const uint32_t buf = stage_buf + (uint32_t)(cur_buf * 4096) + (uint32_t)(lane * 128);
                     const int j0 = (s & 3) * 2;                 // 16-byte piece of the 128-byte row
                     st_shared_v4(buf + (uint32_t)(((j0) ^ (lane & 7)) << 4), h0, h1, h2, h3);
                     st_shared_v4(buf + (uint32_t)(((j0 + 1) ^ (lane & 7)) << 4), h4, h5, h6, h7);
@@ -366,25 +453,37 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                     op[1] = make_uint4(h4, h5, h6, h7);
                 }
             };
-            mbar_wait(smem_u32(&tmem_full_bar), 0);
+            mbar_wait(smem_u32(&acc_full_bar[acc]), acc_par);
             tc_fence_after();
-            if (p.epi) fence_proxy_async_smem();
+            if (!PERSIST && p.epi) fence_proxy_async_smem();
             uint32_t va[16], ga[16], vb[16], gb[16];
-            tmem_ld_32x32b_x16(taddr, va);
-            tmem_ld_32x32b_x16(taddr + (uint32_t)half_bn, ga);
-            for (int s = 0; s < nsteps; s += 2) {
-                tc_wait_ld();  // va / ga = step s
-                tmem_ld_32x32b_x16(taddr + (uint32_t)((s + 1) * 16), vb);
-                tmem_ld_32x32b_x16(taddr + (uint32_t)(half_bn + (s + 1) * 16), gb);
+            // this warp's steps: the groups of four (s .. s+3), s = 4*half, 4*half + 4*NH, ...
+            auto next_step = [](int s) { return (s & 3) == 3 ? s + 1 + 4 * (NH - 1) : s + 1; };
+            int s = 4 * half;
+            if (s < nsteps) {
+                tmem_ld_32x32b_x16(taddr + (uint32_t)(s * 16), va);
+                tmem_ld_32x32b_x16(taddr + (uint32_t)(half_bn + s * 16), ga);
+            } else {
+                release_acc();
+            }
+            while (s < nsteps) {
+                tc_wait_ld();  // va / ga = step s (even)
+                const int s1 = s + 1, s2 = next_step(s1);
+                tmem_ld_32x32b_x16(taddr + (uint32_t)(s1 * 16), vb);
+                tmem_ld_32x32b_x16(taddr + (uint32_t)(half_bn + s1 * 16), gb);
                 step(va, ga, s);
                 tc_wait_ld();  // vb / gb = step s+1
-                if (s + 2 < nsteps) {
-                    tmem_ld_32x32b_x16(taddr + (uint32_t)((s + 2) * 16), va);
-                    tmem_ld_32x32b_x16(taddr + (uint32_t)(half_bn + (s + 2) * 16), ga);
+                if (s2 < nsteps) {
+                    tmem_ld_32x32b_x16(taddr + (uint32_t)(s2 * 16), va);
+                    tmem_ld_32x32b_x16(taddr + (uint32_t)(half_bn + s2 * 16), ga);
+                } else {
+                    release_acc();
                 }
-                step(vb, gb, s + 1);
+                step(vb, gb, s1);
+                s = s2;
             }
         }
+        }  // tile loop
         if constexpr (PEER) {
             // the peers' copies (bulk stores and the per-thread stores of an unpaired chunk) must be complete and visible
             // system-wide before the kernel that follows in the stream raises this rank's flag
@@ -396,7 +495,19 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols * NACC);
+}
+
+// Which schedule a shape gets when nobody forces one.  Measured on every layer shape of a denoising step
+// (profiles/r3a_gemm_persist_table.txt: 92.2 ms of one-tile launches -> 84.0 ms all persistent -> 81.0 ms per-shape best):
+// the persistent schedule wins wherever a CTA's life is dominated by set-up, first-load latency and drain (short K:
+// K = 320 GEGLU 546 -> 810 TFLOP/s, qkv 528 -> 754) and loses where two co-resident one-tile CTAs fill the tensor pipe
+// better than one persistent CTA walking two tiles (1 < waves < 2 with long K: the 8x8 / 16x16 levels, up to -40 %).
+bool persistent_by_shape(int ntiles, int nkb, int bn) {
+    const double waves = (double)ntiles / gcb_sm_count();
+    if (bn == 256) return waves > 1.0;
+    if (bn == 160) return (waves > 1.0 && nkb <= 20) || (waves >= 2.0 && nkb <= 90) || waves >= 6.0;
+    return false;   // BN = 128 / 64 are only chosen for problems of about one wave
 }
 
 int choose_bn(int M, int N, int act) {
@@ -475,6 +586,13 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
                                     direct_epilogue, nullptr, 0, 0, stream);
 }
 
+namespace {
+// Schedule of the next launches: -1 = by shape (product default), 0 = one tile per CTA, 1 = persistent wherever it is
+// built (TMA-store epilogue, no peers).  Set through gcb_conv2d_nhwc_fwd's impl argument (A/B tools) or GCB_GEMM_PERSIST.
+int g_schedule = -1;
+}  // namespace
+void gcb_gemm_tc_set_schedule(int schedule) { g_schedule = schedule; }
+
 // peer_y[0..n_peer): the same output tensor in the peers' memory (every staged tile is stored there as well).  Needs the
 // TMA-store epilogue with complete 64-column groups: Cout % 64 == 0, no GEGLU, no direct epilogue.  Only output columns
 // >= peer_col_min (a multiple of 64) travel to the peers.
@@ -493,15 +611,47 @@ int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, con
     p.W = W;
     p.HW = H * W;
     p.BN = choose_bn((int)M, Cout, act);
+    p.n_tiles = gcb_cdiv(Cout, p.BN);
+    p.ntiles = p.n_tiles * (int)gcb_cdiv(M, BM);
     p.kb_per_tap = (ksize == 3) ? Cin / BK : gcb_cdiv(Cin, BK);
     p.nkb = taps * p.kb_per_tap;
     const int stage_bytes = A_STAGE_BYTES + p.BN * BK * 2;
-    int budget = 110 * 1024;  // two CTAs per SM: one tile's epilogue overlaps the other's main loop
-    if (const char* e = getenv("GCB_GEMM_SMEM_KB")) budget = atoi(e) * 1024;
-    p.stages = budget / stage_bytes;
-    if (p.stages < 2) p.stages = 2;
-    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-    if (p.stages > p.nkb) p.stages = p.nkb < 2 ? 2 : p.nkb;
+    p.ldy = (act == GCB_ACT_GEGLU) ? Cout / 2 : Cout;
+    // default: 32x64 output tiles staged in shared memory + TMA store; GCB_GEMM_TCGEN05_DIRECT keeps the round-1
+    // per-thread row stores for A/B measurements
+    p.epi = (!direct_epilogue && p.ldy >= 64) ? 1 : 0;
+    static int env_schedule = -2;
+    if (env_schedule == -2) {
+        const char* e = getenv("GCB_GEMM_PERSIST");
+        env_schedule = e ? atoi(e) : -1;
+    }
+    const int schedule = g_schedule >= 0 ? g_schedule : env_schedule;
+    bool persist = p.epi && n_peer == 0;
+    if (persist && schedule == 0) persist = false;
+    if (persist && schedule < 0) persist = persistent_by_shape(p.ntiles, p.nkb, p.BN);
+    size_t smem;
+    if (persist) {
+        // one CTA per SM: the ring takes what 227 KB leave after the epilogue staging (8 warps x 1 or 2 x 4 KB); it is
+        // NOT clipped to the K blocks of one tile - the producer runs ahead into the next tile
+        const int avail = 227 * 1024 - 1024 - 512;   // alignment slack, static barriers
+        p.stage_bufs = 2;
+        p.stages = (avail - 8 * 2 * 4096) / stage_bytes;
+        if (p.stages < 4) {
+            p.stage_bufs = 1;
+            p.stages = (avail - 8 * 4096) / stage_bytes;
+        }
+        if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+        p.stage_off = (uint32_t)(p.stages * stage_bytes);
+        smem = (size_t)p.stages * stage_bytes + (size_t)8 * p.stage_bufs * 4096 + 1024;
+    } else {
+        int budget = 110 * 1024;  // two CTAs per SM: one tile's epilogue overlaps the other's main loop
+        if (const char* e = getenv("GCB_GEMM_SMEM_KB")) budget = atoi(e) * 1024;
+        p.stages = budget / stage_bytes;
+        if (p.stages < 2) p.stages = 2;
+        if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+        if (p.stages > p.nkb) p.stages = p.nkb < 2 ? 2 : p.nkb;
+        smem = (size_t)p.stages * stage_bytes + 1024;
+    }
     p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
     p.idesc = make_idesc_f16(BM, p.BN, 0, 0);
     p.bias = (const __half*)bias;
@@ -509,11 +659,7 @@ int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, con
     p.rowvec_ld = rowvec_ld;
     p.residual = (const __half*)residual;
     p.y = (__half*)y;
-    p.ldy = (act == GCB_ACT_GEGLU) ? Cout / 2 : Cout;
     p.act = act;
-    // default: 32x64 output tiles staged in shared memory + TMA store; GCB_GEMM_TCGEN05_DIRECT keeps the round-1
-    // per-thread row stores for A/B measurements
-    p.epi = (!direct_epilogue && p.ldy >= 64) ? 1 : 0;
 
     CUtensorMap tmA, tmB, tmY;
     int rc;
@@ -550,13 +696,13 @@ int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, con
             tmY = tmB;
         }
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     static unsigned long long configured = 0;   // one bit per device ordinal
     if (gcb_first_use_on_device(configured)) {
-        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        GCB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
     }
-    dim3 grid(gcb_cdiv(Cout, p.BN), gcb_cdiv(M, BM));
+    const dim3 grid(persist ? (unsigned)(p.ntiles < gcb_sm_count() ? p.ntiles : gcb_sm_count()) : (unsigned)p.ntiles);
     if (n_peer > 0) {
         GCB_CHECK_ARG(n_peer <= MAX_PEER_MAPS && peer_y, "at most %d peer outputs", MAX_PEER_MAPS);
         GCB_CHECK_ARG(p.epi && act != GCB_ACT_GEGLU && Cout % 64 == 0,
@@ -574,10 +720,13 @@ int gcb_gemm_tc_launch_peers(const void* x, const void* w, const void* bias, con
             if (rc != GCB_OK) return rc;
             pm.y[q] = (__half*)peer_y[q];
         }
-        gemm_tc_kernel<true><<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p, pm);
+        gemm_tc_kernel<true, false><<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p, pm);
+    } else if (persist) {
+        NoPeers np{0};
+        gemm_tc_kernel<false, true><<<grid, 320, smem, stream>>>(tmA, tmB, tmY, p, np);
     } else {
         NoPeers np{0};
-        gemm_tc_kernel<false><<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p, np);
+        gemm_tc_kernel<false, false><<<grid, 192, smem, stream>>>(tmA, tmB, tmY, p, np);
     }
     GCB_LAUNCH_CHECK();
     return GCB_OK;

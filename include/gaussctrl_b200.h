@@ -48,6 +48,8 @@ int gcb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 #define GCB_GEMM_TCGEN05 0 /* TMA + tcgen05.mma + TMEM accumulators */
 #define GCB_GEMM_MMA_SYNC 1 /* legacy mma.sync path kept for bring-up comparison */
 #define GCB_GEMM_TCGEN05_DIRECT 2 /* tcgen05 main loop with the round-1 epilogue (per-thread row stores): A/B only */
+#define GCB_GEMM_TCGEN05_PERSISTENT 3 /* force the persistent schedule (one CTA per SM, two TMEM accumulators): A/B only */
+#define GCB_GEMM_TCGEN05_ONE_TILE 4 /* force the one-tile-per-CTA schedule: A/B only */
 
 /* Implicit-GEMM convolution / linear layer, fp16 in/out, fp32 accumulate.
  *   x        [B,H,W,Cin]                 (Linear: B=1,H=1,W=M rows)

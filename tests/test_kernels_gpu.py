@@ -62,7 +62,11 @@ GEMM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma_sync", "tcgen05_direct_epilogue"])
+GEMM_IMPLS = dict(argvalues=[0, 1, 2, 3, 4],
+                  ids=["tcgen05", "mma_sync", "tcgen05_direct_epilogue", "tcgen05_persistent", "tcgen05_one_tile"])
+
+
+@pytest.mark.parametrize("impl", **GEMM_IMPLS)
 @pytest.mark.parametrize("case", GEMM_CASES)
 def test_conv_gemm(ops, impl, case):
     B, H, W, Cin, Cout, k = case
@@ -79,7 +83,7 @@ def test_conv_gemm(ops, impl, case):
         ops.set_gemm_impl(0)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma_sync", "tcgen05_direct_epilogue"])
+@pytest.mark.parametrize("impl", **GEMM_IMPLS)
 def test_conv_epilogues(ops, impl):
     ops.set_gemm_impl(impl)
     try:
@@ -123,7 +127,7 @@ def test_tma_store_epilogue_equals_direct_epilogue(ops, case):
     rv = _rand((B, Cout), 15) if has_rv else None
     outs = []
     try:
-        for impl in (0, 2):
+        for impl in (0, 2, 3, 4):   # product default, per-thread stores, persistent schedule, one tile per CTA
             ops.set_gemm_impl(impl)
             y = torch.full((B, H, W, co), float("nan"), dtype=torch.float16, device="cuda")  # every element must be written
             ops.conv2d(x, w, bias, k, act=act, rowvec=rv, rowvec_ld=Cout if has_rv else 0, residual=res, out=y)
@@ -131,11 +135,56 @@ def test_tma_store_epilogue_equals_direct_epilogue(ops, case):
             outs.append(y)
     finally:
         ops.set_gemm_impl(0)
-    assert not torch.isnan(outs[0].float()).any() and not torch.isnan(outs[1].float()).any()
-    assert torch.equal(outs[0], outs[1])
+    for o in outs:
+        assert not torch.isnan(o.float()).any()
+        assert torch.equal(outs[0], o)
     if act != 2:
         rel, mx = _relerr(outs[0], _conv_ref(x, w, bias, k, rowvec=rv, residual=res, act=act))
         assert rel < 2e-3, (rel, mx)
+
+
+@pytest.mark.parametrize("case", [
+    # B, H, W, Cin, Cout, k, act, residual, rowvec - every CTA of the persistent schedule walks several tiles
+    (24, 64, 64, 320, 320, 1, 0, True, False),     # 1 536 tiles of 128 x 160 (unpaired 32-column chunk), 5 K blocks
+    (1, 1, 24576, 320, 2560, 1, 2, False, False),  # GEGLU, 1 920 tiles of 128 x 256, ring of 4 stages across tiles
+    (8, 64, 64, 320, 320, 3, 1, True, True),       # conv3x3 + every epilogue term, 512 tiles, 45 K blocks
+    (24, 32, 32, 640, 640, 1, 0, False, False),    # BN = 128: one group per epilogue warp
+    (9, 32, 32, 640, 1920, 1, 0, False, False),    # ragged tile count: 72 x 8 = 576 tiles on 148 CTAs
+    (7, 64, 64, 320, 64, 1, 1, False, True),       # BN = 64: the second column half has nothing to drain
+    (1, 1, 20000, 1280, 320, 1, 0, True, False),   # M not a multiple of 128, K = 1280
+])
+def test_persistent_schedule_equals_one_tile(ops, case):
+    """The persistent schedule (ring across tiles, two TMEM accumulators, eight epilogue warps) and the one-tile
+    schedule produce bit-identical tensors: same MMA order per tile, same epilogue arithmetic."""
+    B, H, W, Cin, Cout, k, act, has_res, has_rv = case
+    x = _rand((B, H, W, Cin), 21)
+    w = _rand((Cout, k * k * Cin), 22, scale=1.0 / math.sqrt(k * k * Cin))
+    bias = _rand((Cout,), 23)
+    co = Cout // 2 if act == 2 else Cout
+    res = _rand((B, H, W, co), 24) if has_res else None
+    rv = _rand((B, Cout), 25) if has_rv else None
+    outs = []
+    try:
+        for impl in (3, 4, 3):
+            ops.set_gemm_impl(impl)
+            y = torch.full((B, H, W, co), float("nan"), dtype=torch.float16, device="cuda")
+            ops.conv2d(x, w, bias, k, act=act, rowvec=rv, rowvec_ld=Cout if has_rv else 0, residual=res, out=y)
+            torch.cuda.synchronize()
+            outs.append(y)
+    finally:
+        ops.set_gemm_impl(0)
+    assert not torch.isnan(outs[0].float()).any()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    if act != 2 and k == 1:
+        xs, ys = x.reshape(-1, Cin)[:4096].float(), outs[0].reshape(-1, co)[:4096].float()
+        ref = xs @ w.float().t() + bias.float()
+        if has_rv:
+            ref = ref + rv[0].float()
+        if act == 1:
+            ref = torch.nn.functional.silu(ref)
+        if has_res:
+            ref = ref + res.reshape(-1, co)[:4096].float()
+        assert _relerr(ys, ref)[0] < 2e-3
 
 
 @pytest.mark.parametrize("C", [320, 640, 1280])

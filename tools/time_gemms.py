@@ -1,6 +1,7 @@
 """Per-shape timing of every GEMM / implicit-GEMM conv of one denoising step (reference pass, CFG batch 8, + one view
-batch, CFG batch 2*vb) with CUDA events: default epilogue (TMA store) vs GCB_GEMM_TCGEN05_DIRECT (round-1 per-thread
-row stores).  Prints a table sorted by time and writes gpurun_out/gemm_table.json."""
+batch, CFG batch 2*vb) with CUDA events, two implementations side by side (GCB_TIME_IMPLS="old,new" impl ids of
+include/gaussctrl_b200.h; default "4,3": one tile per CTA vs the persistent schedule; "2,0": round-1 per-thread row
+stores vs the product default).  Prints a table sorted by time and writes gpurun_out/gemm_table.json."""
 import collections, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,6 +11,7 @@ from gaussctrl_b200.diffusion import SD15Denoiser, cached_crossview_plan, litera
 from gaussctrl_b200.sd15_spec import synthetic_weights
 
 vb = int(os.environ.get("GCB_PROFILE_VB", "12"))
+IMPL_OLD, IMPL_NEW = (int(v) for v in os.environ.get("GCB_TIME_IMPLS", "4,3").split(","))
 unet, cnet, _ = synthetic_weights(0, with_vae=False)
 den = SD15Denoiser(unet, cnet, "cuda")
 g = torch.Generator().manual_seed(0)
@@ -69,22 +71,24 @@ for shape, n in counts.items():
     flops = 2.0 * M * K * Cout
     co = Cout // 2 if act == GCB_ACT_GEGLU else Cout
     byts = 2.0 * (M * Cin + Cout * K + M * co * (2 if hres else 1))
-    us_new, y_new = time_shape(shape, GCB_GEMM_TCGEN05)
-    us_old, y_old = time_shape(shape, GCB_GEMM_TCGEN05_DIRECT)
+    us_new, y_new = time_shape(shape, IMPL_NEW)
+    us_old, y_old = time_shape(shape, IMPL_OLD)
     same = bool(torch.equal(y_new, y_old)) if y_new.shape == y_old.shape else False
     rows.append(dict(shape=list(shape), count=n, us_tma=us_new, us_direct=us_old, tflops_tma=flops / us_new / 1e6,
                      tflops_direct=flops / us_old / 1e6, hbm_floor_us=byts / 6.5e6, total_us_tma=n * us_new,
                      total_us_direct=n * us_old, bit_identical=same))
 rows.sort(key=lambda r: -r["total_us_direct"])
 tot_new, tot_old = sum(r["total_us_tma"] for r in rows), sum(r["total_us_direct"] for r in rows)
-print(f"{'B':>3} {'HxW':>7} {'Cin':>5} {'Cout':>5} k act b/rv/res  n | us direct -> tma  | TF/s direct -> tma | HBM floor us | share(direct) same")
+print(f"{'B':>3} {'HxW':>7} {'Cin':>5} {'Cout':>5} k act b/rv/res  n | us old -> new     | TF/s old -> new    | HBM floor us | share(old) same")
 for r in rows:
     B, H, W, Cin, Cout, k, act, hb, hr, hres = r["shape"]
     print(f"{B:>3} {H:>3}x{W:<3} {Cin:>5} {Cout:>5} {k} {act}   {int(hb)}/{int(hr)}/{int(hres)}   {r['count']:>3} | "
           f"{r['us_direct']:8.1f} -> {r['us_tma']:8.1f} | {r['tflops_direct']:6.0f} -> {r['tflops_tma']:6.0f} | "
           f"{r['hbm_floor_us']:8.1f} | {r['total_us_direct'] / tot_old:6.1%} {r['bit_identical']}")
-print(f"GEMM time per 36 views x 1 DDIM step: direct {tot_old / 1e3:.2f} ms -> tma {tot_new / 1e3:.2f} ms; "
+best = sum(min(r["total_us_tma"], r["total_us_direct"]) for r in rows)
+print(f"impl {IMPL_OLD} -> impl {IMPL_NEW}; per-shape best of both: {best / 1e3:.2f} ms")
+print(f"GEMM time per 36 views x 1 DDIM step: old {tot_old / 1e3:.2f} ms -> new {tot_new / 1e3:.2f} ms; "
       f"all outputs bit-identical: {all(r['bit_identical'] for r in rows)}")
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(dict(view_batch=vb, rows=rows, total_ms_direct=tot_old / 1e3, total_ms_tma=tot_new / 1e3),
+json.dump(dict(view_batch=vb, impl_old=IMPL_OLD, impl_new=IMPL_NEW, rows=rows, total_ms_direct=tot_old / 1e3, total_ms_tma=tot_new / 1e3),
           open(os.environ.get("GCB_GEMM_TABLE_OUT", "gpurun_out/gemm_table.json"), "w"), indent=1)
