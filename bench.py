@@ -510,13 +510,21 @@ def main():
             ops.ATTN_EVENTS = None
             roof = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         # (2) ISOLATED: the same launch alone, back to back, against the burst peak
-        qkv = torch.randn((Bq, ATTN_N, 3 * C), device=dev).half()
-        refkv = torch.randn((2 * R, ATTN_N, 3 * C), device=dev).half()
+        # the layout SD15Denoiser gives the kernel: fused q|k|v rows whose V heads are padded to 48 columns, column 40 = 1
+        vs = 48 if getattr(pipe.denoiser, "ones_column", False) else ATTN_D
+        ld = 2 * C + ATTN_HEADS * vs
+        qkv = torch.randn((Bq, ATTN_N, ld), device=dev).half()
+        refkv = torch.randn((2 * R, ATTN_N, ld), device=dev).half()
+        if vs > ATTN_D:
+            for t_ in (qkv, refkv):
+                vv = t_[..., 2 * C:].reshape(t_.shape[0], ATTN_N, ATTN_HEADS, vs)
+                vv[..., ATTN_D:] = 0
+                vv[..., ATTN_D] = 1.0
         rows_i = [[h * vb_eff + f] + [-(h * R + r) - 1 for r in range(4)] for h in range(2) for f in range(vb_eff)]
         idx = torch.tensor(rows_i, dtype=torch.int32, device=dev)
         w = [0.6, 0.1, 0.1, 0.1, 0.1]
-        call = lambda: ops.attention(qkv, 0, 3 * C, qkv, C, 2 * C, 3 * C, refkv, C, 2 * C, 3 * C, Bq, ATTN_N, ATTN_N,  # noqa: E731
-                                     ATTN_HEADS, ATTN_D, idx, w)
+        call = lambda: ops.attention(qkv, 0, ld, qkv, C, 2 * C, ld, refkv, C, 2 * C, ld, Bq, ATTN_N, ATTN_N,  # noqa: E731
+                                     ATTN_HEADS, ATTN_D, idx, w, v_head_stride=vs)
         for _ in range(3):
             call()
         e0, e1 = ev(), ev()

@@ -3,20 +3,27 @@
 //
 //   out[b, i, h, :] = sum_s w_s * softmax_j( q[b,i,h,:] . K_s[j,h,:] * scale ) V_s[j,h,:]      (utils.py:25-37, 88-117)
 //
-// One CTA = NSLOT 128-row query slots of one (batch row, head).  Warp roles (32 * (4 NSLOT + 2) threads):
-//   warps 4t..4t+3  : softmax of slot t - one query row per thread, S read from TMEM (tcgen05.ld), exp2 on the
-//                     MUFU, row sums in fp32 registers, P written back to TMEM (tcgen05.st) as packed halves: the
-//                     A operand of P V.  Probabilities never touch shared memory or HBM.
-//   warp 4 NSLOT    : TMA producer (Q once; K and V tiles of BN keys through mbarrier rings)
-//   warp 4 NSLOT + 1: TMEM allocator + tcgen05.mma issuer (one elected lane):
+// One CTA = NSLOT 128-row query slots of one (batch row, head).  Warp roles (32 * (4 RS NSLOT + 2) threads, RS =
+// threads per query row):
+//   warps 4 RS t ..   : softmax of slot t - S read from TMEM (tcgen05.ld), exp2, P written back to TMEM (tcgen05.st) as
+//                       packed halves: the A operand of P V.  Probabilities never touch shared memory or HBM.
+//                       RS = 1: one query row per thread.  RS = 2 (head dim 40): the two warps that own a TMEM lane
+//                       quarter split the tile's keys (64 each) and exchange the tile max through shared memory + a
+//                       64-thread named barrier - four softmax warps per scheduler instead of two.
+//   warp 4 RS NSLOT   : TMA producer (Q once; K and V tiles of BN keys through mbarrier rings)
+//   warp 4 RS NSLOT + 1: TMEM allocator + tcgen05.mma issuer (one elected lane):
 //                       S   = Q K^T    M128 x N(BN) x K(DK)   both operands K-major, 128B-swizzled 64-column TMA boxes
 //                       O  += P V      M128 x N(NV) x K(BN)   A = P from TMEM, B = V MN-major straight from its row-major tile
 // Head dim 40: two slots, BN=128, DK=48 - the Q/K boxes are 64 columns wide; columns 40..47 of Q are zeroed in smem so
 //   the neighbouring head's columns that ride along in K contribute nothing; NV=48 (columns 40..47 of O are don't-care).
-//   The kernel is bound by the MUFU (exp2: 16/clk/SM); each scheduler's MUFU is fed by the two softmax warps resident on
-//   it, one per slot.  Measured alternatives (profiles/r2_attn_ab.md): a third slot with BN=64 (TMEM: 3 x (64 S + 32 P +
-//   48 O) = 432 columns) runs at 405 TFLOP/s against 530 - and so does BN=64 with two slots, i.e. the per-tile fixed
-//   cost of the smaller tile eats the gain; a four-piece P store 495; issuing a slot's next QK^T after its own PV 442.
+//   With every exponential on the MUFU (exp2: 16/clk/SM) and one thread per row the kernel sat at 530 TFLOP/s: 73 % of
+//   its MUFU floor, the two softmax warps of a scheduler leaving the pipe idle whenever both were outside their
+//   exponential phase (profiles/r1i_attn_source_summary.md).  Round 3 (profiles/r3_attn.md): (a) 3 of every 8 key pairs
+//   take a packed-half polynomial on the FMA/ALU pipes instead (ex2_hpoly; the row sums then come out of the P V
+//   product through a ones column of V) - 583 TFLOP/s; (b) two threads per row, i.e. four softmax warps per scheduler.
+//   Measured and rejected before (profiles/r2_attn_ab.md): a third slot with BN=64 405 TFLOP/s, BN=64 with two slots
+//   405, four-piece P store 495, MUFU ping-pong 500, other MMA issue orders 442-486, ex2.approx.f16x2 (two MUFU ops
+//   in SASS) 428, fp32 polynomial 485, setmaxnreg 232/40 split 529 (r3d).
 // Head dim 80: two slots, BN=64, DK=80 (two boxes: 64 + 16 used columns), NV=80 (two MN atoms of V).
 // Online softmax with lazy rescaling (threshold 2^8): the O correction (TMEM load-scale-store) is rare.  Sources are
 // processed back to back; at the end of each source the slot folds O * w_s / l into an fp32 accumulator (shared
@@ -33,67 +40,36 @@ namespace {
 constexpr int MAX_SRC = 8;
 constexpr int BM = 128;  // query rows per slot
 constexpr float RESCALE_THRESHOLD = 8.f;
-#ifndef GCB_ATTN_LAG
-#define GCB_ATTN_LAG 0
-#endif
-#ifndef GCB_ATTN_SPLIT_LD
-#define GCB_ATTN_SPLIT_LD 0
-#endif
-#ifndef GCB_ATTN_SPLIT_ST
-#define GCB_ATTN_SPLIT_ST 1
-#endif
-// The non-MUFU part of a tile (BN = 128 only; profiles/r1i_attn_source_summary.md), A/B in one process with
-// tools/ab_attn_libs.py at B=24, N=4096, d=40 (profiles/r1o_ab_attn_split.txt; outputs bit-identical in all four builds):
-//   SPLIT_ST (ON): the first 64 packed probabilities are stored (tcgen05.st) after half of the exponentials; the p_free
-//             spin in between also splits the basic block, so ptxas can no longer sink all 64 packs behind the last
-//             ex2: 487.5 -> 538.1 TFLOP/s (+10 %).
-//   SPLIT_LD (off): the second half of S still loading from TMEM while the row max of the first half is taken:
-//             484.7 TFLOP/s alone, 535.7 with SPLIT_ST - no gain, the TMEM-load latency is not what the max phase waits on.
-//   SPLIT_ST = 4 (not measured yet - the round's GPU budget ended): four pieces of 16 packed registers; the extra block
-//             boundaries come from re-waiting the already completed p_free phase (returns at once, but is a branch).
-#ifndef GCB_ATTN_PINGPONG
-#define GCB_ATTN_PINGPONG 0
-#endif
-// MUFU ping-pong (two-slot kernels): the softmax warps of slot 0 and slot 1 that share a scheduler (same TMEM lane
-// quarter) pass a token through a pair of named barriers so that only ONE of them is in its exponential phase at a
-// time - the other does its non-MUFU work (wait for S, TMEM load, row max, pack, store) meanwhile.  Without it the two
-// exponential phases mostly coincide (each then runs at half the MUFU rate) and so do the non-MUFU phases (pipe idle).
-constexpr bool ATTN_PINGPONG = GCB_ATTN_PINGPONG != 0;
-constexpr bool ATTN_SPLIT_LD = GCB_ATTN_SPLIT_LD != 0, ATTN_SPLIT_ST = GCB_ATTN_SPLIT_ST != 0;
-constexpr bool ATTN_SPLIT_ST4 = GCB_ATTN_SPLIT_ST == 4;
-constexpr int ATTN_LAG = GCB_ATTN_LAG;  // 0 = off, 1 = slot 0 signals after its row max, 2 = after half of its exponentials
 
 template <int D_>
 struct Cfg;
 template <>
 struct Cfg<40> {
-#if defined(GCB_ATTN40_THREE_SLOTS)   // A/B (r2j): three slots, BN = 64 - 405 TFLOP/s against 530 for the default
-    static constexpr int D = 40, BN = 64, DK = 48, NV = 48, BOXES = 1, NSLOT = 3, STAGES = 6;
-    static constexpr uint32_t TM_S = 0, TM_P = 192, TM_O = 288, TM_O_STRIDE = 48, TM_ACC = 0;
-#elif defined(GCB_ATTN40_BN64_TWO)    // A/B (r2j): BN = 64 with two slots - also 405: the tile size costs, not the slots
-    static constexpr int D = 40, BN = 64, DK = 48, NV = 48, BOXES = 1, NSLOT = 2, STAGES = 6;
-    static constexpr uint32_t TM_S = 0, TM_P = 192, TM_O = 288, TM_O_STRIDE = 48, TM_ACC = 0;
-#else
     static constexpr int D = 40, BN = 128, DK = 48, NV = 48, BOXES = 1, NSLOT = 2, STAGES = 4;
     static constexpr uint32_t TM_S = 0, TM_O = 256, TM_O_STRIDE = 64, TM_P = 384, TM_ACC = 0;
-#endif
     static constexpr bool ZERO_Q_PAD = true, ACC_IN_TMEM = false;
-    // exponentials per 8 evaluated by the FMA-pipe polynomial instead of the MUFU.  Measured on B200 (r1): 3/8 makes
-    // the kernel SLOWER (546 -> 485 TFLOP/s): 3-register FFMA/FADD issue at half rate per SM sub-partition, so the
-    // ~7-instruction polynomial costs more FMA-pipe time than the MUFU slot it frees.  Kept at 0.
-    static constexpr int POLY_OF_8 = 0;
-#ifdef GCB_ATTN_EXP_F16X2
-    static constexpr bool EXP_F16X2 = true;
+    // threads per query row: each takes BN / ROWSPLIT keys of every tile (see the header).  Two threads per row (four
+    // softmax warps per scheduler, 96 registers per thread) measured 545-570 TFLOP/s against 620-634 for one: 19 % more
+    // instructions per key (per-warp fixed work twice, the max exchange) at the same ~64 % issue-slot use (r3e/r3g/r3j).
+#ifdef GCB_ATTN40_ROWSPLIT
+    static constexpr int ROWSPLIT = GCB_ATTN40_ROWSPLIT;
 #else
-    static constexpr bool EXP_F16X2 = false;
+    static constexpr int ROWSPLIT = 1;
+#endif
+    // key pairs out of every 8 whose exponentials run as ONE packed-half polynomial on the FMA / ALU pipes (ex2_hpoly)
+    // instead of two MUFU.EX2 + one F2FP; only when the row sums come out of the P V product (V ones column).
+    // 2 / 3 / 4 of 8 measure the same (628 / 623 / 617 TFLOP/s, r3h), 5 of 8: 575, 6 of 8: 480 (HFMA2 issues at half rate)
+#ifdef GCB_ATTN_HPOLY
+    static constexpr int HPOLY_OF_8 = GCB_ATTN_HPOLY;
+#else
+    static constexpr int HPOLY_OF_8 = 3;
 #endif
 };
 template <>
 struct Cfg<80> {
     static constexpr int D = 80, BN = 64, DK = 80, NV = 80, BOXES = 2, NSLOT = 2, STAGES = 4;
     static constexpr bool ZERO_Q_PAD = false, ACC_IN_TMEM = true;
-    static constexpr int POLY_OF_8 = 0;
-    static constexpr bool EXP_F16X2 = false;
+    static constexpr int ROWSPLIT = 1, HPOLY_OF_8 = 0;
     static constexpr uint32_t TM_S = 0, TM_O = 128, TM_O_STRIDE = 80, TM_P = 288, TM_ACC = 352;
 };
 
@@ -114,15 +90,17 @@ template <int D_>
 struct __align__(1024) Smem {
     using C = Cfg<D_>;
     static constexpr uint32_t QBOX = BM * 128, KVBOX = C::BN * 128;
-    static constexpr int STAGES = C::STAGES, NSLOT = C::NSLOT;
+    static constexpr int STAGES = C::STAGES, NSLOT = C::NSLOT, RS = C::ROWSPLIT;
     uint8_t q[NSLOT][C::BOXES][QBOX];
     uint8_t k[STAGES][C::BOXES][KVBOX];
     uint8_t v[STAGES][C::BOXES][KVBOX];
     float acc[C::ACC_IN_TMEM ? 1 : NSLOT][C::ACC_IN_TMEM ? 1 : C::D][C::ACC_IN_TMEM ? 4 : BM];  // [slot][column][row]
+    // row split: the tile max (by tile parity) and the row sum (by source parity) of each thread of a row
+    float xmax[RS > 1 ? NSLOT : 1][2][RS > 1 ? RS : 1][RS > 1 ? BM : 4];
+    float xsum[RS > 1 ? NSLOT : 1][2][RS > 1 ? RS : 1][RS > 1 ? BM : 4];
     uint64_t q_full, q_ready;
     uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
     uint64_t s_full[NSLOT], s_free[NSLOT], p_ready[NSLOT], p_free[NSLOT], o_free[NSLOT];
-    uint64_t lag_bar;
     uint32_t tmem_base;
 };
 
@@ -132,46 +110,42 @@ __device__ __forceinline__ float ex2_f32(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// 2^x on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax, max rel. error 7.5e-5 - well below the fp16
-// rounding of P): used for a fraction of the elements so the MUFU (16 ex2/clk/SM) stops being the limiter at d=40.
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -125.f);
-    const float fi = x + 12582912.f;  // 1.5 * 2^23: round(x) lands in the low mantissa bits
-    const float f = x - (fi - 12582912.f);  // [-0.5, 0.5]
-    float r = fmaf(f, 0.0551716648f, 0.2426111251f);
-    r = fmaf(r, f, 0.6932609677f);
-    r = fmaf(r, f, 0.9999280572f);
-    return __int_as_float(__float_as_int(r) + (__float_as_int(fi) << 23));
-}
-__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
-    uint32_t y;
-    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-    return y;
-}
 __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
     uint32_t y;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
     return y;
 }
-// mbarrier arrive whose address carries a (zero) data dependency on `dep`, so that neither nvcc nor ptxas can move it
-// ahead of the instruction that produces `dep`:  (dep >> 31) & (~dep >> 31) == 0 for every dep.
-__device__ __forceinline__ void lag_arrive(uint32_t bar, uint32_t dep) {
-    asm volatile(
-        "{\n\t.reg .b32 a, b;\n\t"
-        "shr.u32 a, %1, 31;\n\t"
-        "not.b32 b, %1;\n\t"
-        "shr.u32 b, b, 31;\n\t"
-        "and.b32 a, a, b;\n\t"
-        "add.u32 a, a, %0;\n\t"
-        "mbarrier.arrive.shared::cta.b64 _, [a];\n\t}"
-        ::"r"(bar), "r"(dep)
-        : "memory");
+// 2^x for a PAIR of keys in packed-half arithmetic: 11 FMA/ALU-pipe instructions per pair, no MUFU, and the result is
+// already the packed fp16 pair the P V product consumes.
+//   h  = fp16x2(x), clamped at -15            (x <= ~8: the lazy-rescale threshold; below -15 the probability is 0)
+//   fi = h + 1551   (= 1536 + 15: in [1024, 2048) the fp16 ulp is 1, so fi = 1551 + round(h), exactly)
+//   f  = h - (fi - 1551)  in [-0.5, 0.5], exact
+//   2^n: the low 5 bits of fi's bit pattern 0x660F + n are n + 15 = the biased fp16 exponent: (fi << 10) & 0x7C00
+//   2^f: degree-3 Horner in fp16, coefficients chosen for the fp16 evaluation: over EVERY fp16 f in [-0.5, 0.5] the max
+//        rel. error is 5.6e-4, rms 2.05e-4, mean -3e-8 - the correctly rounded fp16 of the exact value has 4.9e-4 /
+//        2.03e-4 (tools/fit_hpoly.py)
+__device__ __forceinline__ uint32_t ex2_hpoly(float lo, float hi) {
+    uint32_t h, r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+    asm("{\n\t.reg .b32 h, fi, n, f, t, r;\n\t"
+        "max.f16x2 h, %1, %2;\n\t"
+        "add.rn.f16x2 fi, h, %3;\n\t"
+        "sub.rn.f16x2 n, fi, %3;\n\t"
+        "sub.rn.f16x2 f, h, n;\n\t"
+        "shl.b32 t, fi, 10;\n\t"
+        "and.b32 t, t, 0x7C007C00;\n\t"
+        "fma.rn.f16x2 r, f, %4, %5;\n\t"
+        "fma.rn.f16x2 r, r, f, %6;\n\t"
+        "fma.rn.f16x2 r, r, f, %7;\n\t"
+        "mul.rn.f16x2 %0, r, t;\n\t}"
+        : "=r"(r)
+        : "r"(h), "r"(0xCB80CB80u), "r"(0x660F660Fu), "r"(0x2B082B08u), "r"(0x33C033C0u), "r"(0x398C398Cu),
+          "r"(0x3C003C00u));
+    return r;
 }
+__device__ __forceinline__ constexpr bool hpoly_pair(int pair, int of8) { return of8 > 0 && ((pair * of8) & 7) < of8; }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
@@ -208,7 +182,6 @@ __device__ __forceinline__ void tmem_st32_from(uint32_t taddr, const uint32_t (&
           "r"(r[OFF + 30]), "r"(r[OFF + 31])
         : "memory");
 }
-
 template <int OFF, int NR>
 __device__ __forceinline__ void tmem_st16_from(uint32_t taddr, const uint32_t (&r)[NR]) {
     asm volatile(
@@ -219,18 +192,54 @@ __device__ __forceinline__ void tmem_st16_from(uint32_t taddr, const uint32_t (&
           "r"(r[OFF + 12]), "r"(r[OFF + 13]), "r"(r[OFF + 14]), "r"(r[OFF + 15])
         : "memory");
 }
+// NR/32 x tcgen05.ld.x32 of NR consecutive columns
+template <int NR>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NR]) {
+    static_assert(NR == 32 || NR == 64 || NR == 128, "32, 64 or 128 score columns per thread");
+    tmem_ld32_into<0>(taddr, r);
+    if constexpr (NR >= 64) tmem_ld32_into<(NR >= 64 ? 32 : 0)>(taddr + 32, r);
+    if constexpr (NR >= 128) {
+        tmem_ld32_into<(NR >= 128 ? 64 : 0)>(taddr + 64, r);
+        tmem_ld32_into<(NR >= 128 ? 96 : 0)>(taddr + 96, r);
+    }
+}
+// NP packed registers (= 2 NP keys) of P, stored from r[OFF ..]
+template <int OFF, int NP, int NR>
+__device__ __forceinline__ void tmem_st_packed(uint32_t taddr, const uint32_t (&r)[NR]) {
+    static_assert(NP == 16 || NP == 32, "16 or 32 packed registers per store");
+    if constexpr (NP == 32) tmem_st32_from<OFF>(taddr, r);
+    else tmem_st16_from<OFF>(taddr, r);
+}
+
+// One MMA-issuing warp per slot (default) or one for the whole CTA (GCB_ATTN_ONE_MMA_WARP: A/B).  With a single in-order
+// issuer the QK^T of slot 0's next tile queues behind the P V of slot 1's previous one, which waits for slot 1's
+// softmax: the ncu source view (profiles/r3_attn.md) showed the softmax warps spending 21 % of their time waiting
+// for S.  A warp per slot issues S(t, i+1) as soon as slot t has read S(t, i).
+#ifdef GCB_ATTN_ONE_MMA_WARP
+constexpr bool ATTN_MMA_PER_SLOT = false;
+#else
+constexpr bool ATTN_MMA_PER_SLOT = true;
+#endif
+template <int D_>
+constexpr int attn_threads() {
+    return 32 * (4 * Cfg<D_>::NSLOT * Cfg<D_>::ROWSPLIT + 1 + (ATTN_MMA_PER_SLOT ? Cfg<D_>::NSLOT : 1));
+}
 
 template <int D_>
-__global__ void __launch_bounds__(32 * (4 * Cfg<D_>::NSLOT + 2), 1)
+__global__ void __launch_bounds__(attn_threads<D_>(), 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK2,
                const __grid_constant__ CUtensorMap tmV2, const AttnTcParams p) {
     using C = Cfg<D_>;
     using SM = Smem<D_>;
-    constexpr int D = C::D, BN = C::BN, BOXES = C::BOXES, NSLOT = C::NSLOT, STAGES = C::STAGES;
-    constexpr int W_TMA = 4 * NSLOT, W_MMA = 4 * NSLOT + 1;
+    constexpr int D = C::D, BN = C::BN, BOXES = C::BOXES, NSLOT = C::NSLOT, STAGES = C::STAGES, RS = C::ROWSPLIT;
+    constexpr int NSW = 4 * RS;                       // softmax warps per slot
+    constexpr int W_TMA = NSW * NSLOT, W_MMA = NSW * NSLOT + 1;
     constexpr int KSTEPS = C::DK / 16, PV_STEPS = BN / 16, PCOLS = BN / 2;
+    constexpr int CW = BN / RS;                       // score columns (keys) of a tile per softmax thread
     constexpr uint32_t STAGE_BYTES = BOXES * SM::KVBOX;
+    constexpr uint32_t SLOT_THREADS = 32 * NSW;
+    static_assert(RS == 1 || RS == 2, "one or two threads per query row");
     extern __shared__ uint8_t smem_raw[];
     SM& sm = *reinterpret_cast<SM*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
@@ -242,21 +251,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&sm.q_full), 1);
-        mbar_init(smem_u32(&sm.q_ready), 128 * nslot);
+        mbar_init(smem_u32(&sm.q_ready), SLOT_THREADS * nslot);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(smem_u32(&sm.k_full[i]), 1);
-            mbar_init(smem_u32(&sm.k_empty[i]), 1);
+            mbar_init(smem_u32(&sm.k_empty[i]), ATTN_MMA_PER_SLOT ? nslot : 1);   // one commit per issuing warp
             mbar_init(smem_u32(&sm.v_full[i]), 1);
-            mbar_init(smem_u32(&sm.v_empty[i]), 1);
+            mbar_init(smem_u32(&sm.v_empty[i]), ATTN_MMA_PER_SLOT ? nslot : 1);
         }
         for (int t = 0; t < NSLOT; ++t) {
             mbar_init(smem_u32(&sm.s_full[t]), 1);
-            mbar_init(smem_u32(&sm.s_free[t]), 128);
-            mbar_init(smem_u32(&sm.p_ready[t]), 128);
+            mbar_init(smem_u32(&sm.s_free[t]), SLOT_THREADS);
+            mbar_init(smem_u32(&sm.p_ready[t]), SLOT_THREADS);
             mbar_init(smem_u32(&sm.p_free[t]), 1);
-            mbar_init(smem_u32(&sm.o_free[t]), 128);
+            mbar_init(smem_u32(&sm.o_free[t]), SLOT_THREADS);
         }
-        mbar_init(smem_u32(&sm.lag_bar), 128);
         mbar_fence_init();
     }
     if (warp == W_MMA) {
@@ -310,16 +318,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             __syncwarp();
         }
-    } else if (warp == W_MMA) {
-        // ===================================================================== MMA issuer (whole warp waits, one elected
-        // lane issues tcgen05.mma / tcgen05.commit)
+    } else if (warp >= W_MMA) {
+        // ===================================================================== MMA issuer(s) (whole warp waits, one
+        // elected lane issues tcgen05.mma / tcgen05.commit)
+        const int my_slot = warp - W_MMA;   // per-slot issuers: the slot this warp serves
         const uint32_t idesc_qk = make_idesc_f16(BM, BN, 0, 0);
         const uint32_t idesc_pv = make_idesc_f16(BM, C::NV, 0, 1);  // B = V, MN-major
         mbar_wait(smem_u32(&sm.q_ready), 0);
         tc_fence_after();
         auto issue_qk = [&](int t, int i) {
             const int st = i % STAGES;
-            if (t == 0) mbar_wait(smem_u32(&sm.k_full[st]), ((uint32_t)(i / STAGES)) & 1u);
+            if (ATTN_MMA_PER_SLOT || t == 0) mbar_wait(smem_u32(&sm.k_full[st]), ((uint32_t)(i / STAGES)) & 1u);
             if (i > 0) mbar_wait(smem_u32(&sm.s_free[t]), ((uint32_t)(i - 1)) & 1u);
             tc_fence_after();
             if (elect_one_sync()) {
@@ -331,14 +340,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tc_mma_ss(tmem + C::TM_S + (uint32_t)(t * BN), qd, kd, idesc_qk, (uint32_t)(ks != 0));
                 }
                 tc_commit(smem_u32(&sm.s_full[t]));
-                if (t == nslot - 1) tc_commit(smem_u32(&sm.k_empty[st]));
+                if (ATTN_MMA_PER_SLOT || t == nslot - 1) tc_commit(smem_u32(&sm.k_empty[st]));
             }
             __syncwarp();
         };
         auto issue_pv = [&](int t, int i) {
             const int s = i / nkt, j = i - s * nkt;
             const int st = i % STAGES;
-            if (t == 0) mbar_wait(smem_u32(&sm.v_full[st]), ((uint32_t)(i / STAGES)) & 1u);
+            if (ATTN_MMA_PER_SLOT || t == 0) mbar_wait(smem_u32(&sm.v_full[st]), ((uint32_t)(i / STAGES)) & 1u);
             mbar_wait(smem_u32(&sm.p_ready[t]), ((uint32_t)i) & 1u);
             if (j == 0 && s > 0) mbar_wait(smem_u32(&sm.o_free[t]), ((uint32_t)(s - 1)) & 1u);
             tc_fence_after();
@@ -351,122 +360,104 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int kk = 0; kk < PV_STEPS; ++kk)
                     tc_mma_ts(o_t, p_t + (uint32_t)(kk * 8), vd0 + (uint64_t)(kk * 128), idesc_pv, (uint32_t)((j | kk) != 0));
                 tc_commit(smem_u32(&sm.p_free[t]));
-                if (t == nslot - 1) tc_commit(smem_u32(&sm.v_empty[st]));
+                if (ATTN_MMA_PER_SLOT || t == nslot - 1) tc_commit(smem_u32(&sm.v_empty[st]));
             }
             __syncwarp();
         };
-        for (int t = 0; t < nslot; ++t) issue_qk(t, 0);
-        // Issue order.  qk(1, i+1) sits behind pv(0, i), which blocks until slot 0 has finished the exponentials of tile
-        // i: slot 1 therefore starts every tile a fixed lag after slot 0.  That coupling is deliberate - with both QK^T
-        // products issued ahead of the PVs (tried in r1j) the slots fall into step, their non-MUFU phases coincide and
-        // the kernel is 6 % SLOWER (518 -> 486 TFLOP/s).  GCB_ATTN_LAG > 0 lengthens the lag instead: qk(1, i+1)
-        // additionally waits until slot 0 has reached a given point of tile i+1 (lag_bar).  Also measured (r1k) and
-        // rejected: 513 -> 427 (signal after the row max) / 434 TFLOP/s (after half of the exponentials) at d=40,
-        // 729 -> 535 at d=80.  The round-1 order below is the measured optimum of the three; kept at 0.
-        if (ATTN_LAG) mbar_wait(smem_u32(&sm.lag_bar), 0);
-        for (int i = 0; i < T; ++i) {
-#if defined(GCB_ATTN_ORDER) && GCB_ATTN_ORDER == 1
-            // A/B: slot t's next QK^T goes out right after ITS OWN PV (it only needs s_free, signalled early in the tile)
-            for (int t = 0; t < nslot; ++t) {
-                issue_pv(t, i);
-                if (i + 1 < T) issue_qk(t, i + 1);
-            }
-#else
-            for (int t = 0; t < nslot; ++t) {
-                if (i + 1 < T) {
-                    if (ATTN_LAG && t == 1) mbar_wait(smem_u32(&sm.lag_bar), ((uint32_t)(i + 1)) & 1u);
-                    issue_qk(t, i + 1);
+        if (ATTN_MMA_PER_SLOT) {
+            if (my_slot < nslot) {
+                issue_qk(my_slot, 0);
+                for (int i = 0; i < T; ++i) {
+                    if (i + 1 < T) issue_qk(my_slot, i + 1);   // needs only K(i+1) and slot's read of S(i)
+                    issue_pv(my_slot, i);
                 }
-                issue_pv(t, i);
             }
-#endif
+        } else {
+            for (int t = 0; t < nslot; ++t) issue_qk(t, 0);
+            // One issuer for both slots: qk(1, i+1) sits behind pv(0, i), which blocks until slot 0 has finished the
+            // exponentials of tile i.  Other single-issuer orders measured in rounds 1-2 (profiles/r2_attn_ab.md): both
+            // QK^T products ahead of the PVs -6 %, an extra lag barrier -17 %, a slot's next QK^T after its own PV -17 %.
+            for (int i = 0; i < T; ++i) {
+                for (int t = 0; t < nslot; ++t) {
+                    if (i + 1 < T) issue_qk(t, i + 1);
+                    issue_pv(t, i);
+                }
+            }
         }
-    } else if ((warp >> 2) < nslot) {
+    } else if (warp / NSW < nslot) {
         // ===================================================================== softmax slots
-        const int t = warp >> 2;         // slot
-        const int wq = warp & 3;         // TMEM lane quarter
-        const int row = wq * 32 + lane;  // row inside the slot
+        const int t = warp / NSW;                 // slot
+        const int wq = warp & 3;                  // TMEM lane quarter (NSW is a multiple of 4)
+        const int ch = (warp % NSW) >> 2;         // which part of the tile's keys (row split)
+        const int row = wq * 32 + lane;           // row inside the slot
         const uint32_t lane_base = ((uint32_t)(wq * 32)) << 16;
-        const uint32_t s_t = tmem + lane_base + C::TM_S + (uint32_t)(t * BN);
+        const uint32_t s_t = tmem + lane_base + C::TM_S + (uint32_t)(t * BN + ch * CW);
         const uint32_t o_t = tmem + lane_base + C::TM_O + (uint32_t)(t * C::TM_O_STRIDE);
-        const uint32_t p_t = tmem + lane_base + C::TM_P + (uint32_t)(t * PCOLS);
+        const uint32_t p_t = tmem + lane_base + C::TM_P + (uint32_t)(t * PCOLS + ch * (CW / 2));
         const uint32_t acc_t = tmem + lane_base + C::TM_ACC + (uint32_t)(t * 80);
         float* acc_row = &sm.acc[C::ACC_IN_TMEM ? 0 : t][0][C::ACC_IN_TMEM ? 0 : row];
+        // named barrier of the RS warps that share this slot's TMEM lane quarter (ids 1 .. 4 NSLOT)
+        const uint32_t pair_bar = 1u + (uint32_t)(t * 4 + wq);
         mbar_wait(smem_u32(&sm.q_full), 0);
-        if (C::ZERO_Q_PAD) {
+        if (C::ZERO_Q_PAD && ch == 0) {
             // zero Q columns 40..47: 16-byte chunk 5 of the 128B-swizzled row
             uint8_t* qrow = sm.q[t][0] + (row >> 3) * 1024 + (row & 7) * 128 + ((5 ^ (row & 7)) * 16);
             *reinterpret_cast<uint4*>(qrow) = make_uint4(0, 0, 0, 0);
             fence_proxy_async();
         }
         mbar_arrive(smem_u32(&sm.q_ready));
-        // named barriers 1..8: "slot t, quarter wq may run its exponentials"; slot 0 goes first
-        const bool pingpong = ATTN_PINGPONG && NSLOT == 2 && nslot == 2;
-        const uint32_t bar_mine = 1u + (uint32_t)(t * 4 + wq), bar_other = 1u + (uint32_t)((t ^ 1) * 4 + wq);
-        if (pingpong && t == 1) named_bar_arrive(bar_other, 64);
+        // combine a per-thread value over the RS threads of a row (same order in every thread: bit-identical)
+        auto row_max = [&](float v, int par) {
+            if constexpr (RS > 1) {
+                // buffer `par` is rewritten two tiles later, behind the barrier of the tile in between, which the other
+                // thread only reaches after it has read this one
+                sm.xmax[t][par][ch][row] = v;
+                named_bar_sync(pair_bar, 32 * RS);
+                return fmaxf(sm.xmax[t][par][0][row], sm.xmax[t][par][1][row]);
+            } else {
+                return v;
+            }
+        };
+        auto row_sum = [&](float v, int par) {
+            if constexpr (RS > 1) {
+                sm.xsum[t][par][ch][row] = v;
+                named_bar_sync(pair_bar, 32 * RS);
+                return sm.xsum[t][par][0][row] + sm.xsum[t][par][1][row];
+            } else {
+                return v;
+            }
+        };
 
         for (int s = 0; s < p.n_act; ++s) {
             float m = -INFINITY;  // running reference max, exp2 domain
-            float l = 0.f;        // running row sum (fp32, of the un-rounded probabilities)
+            float l = 0.f;        // running row sum of this thread's keys (fp32, of the un-rounded probabilities)
             for (int j = 0; j < nkt; ++j) {
                 const int i = s * nkt + j;
                 mbar_wait(smem_u32(&sm.s_full[t]), ((uint32_t)i) & 1u);
                 tc_fence_after();
-                uint32_t sr[BN];
-                tmem_ld32_into<0>(s_t, sr);
-                tmem_ld32_into<32>(s_t + 32, sr);
-                float mxa, mxb, mxc, mxd;
-                if (ATTN_SPLIT_LD && BN == 128) {
-                    tc_wait_ld();  // first 64 columns are in registers
-                    tmem_ld32_into<(BN == 128 ? 64 : 0)>(s_t + 64, sr);
-                    tmem_ld32_into<(BN == 128 ? 96 : 0)>(s_t + 96, sr);
-                    mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
-                    mxd = __uint_as_float(sr[3]);
-#pragma unroll
-                    for (int e = 4; e < 64; e += 8) {
-                        mxa = fmax3(mxa, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
-                        mxb = fmax3(mxb, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
-                        if (e + 4 < 64) {
-                            mxc = fmax3(mxc, __uint_as_float(sr[e + 4]), __uint_as_float(sr[e + 5]));
-                            mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
-                        }
-                    }
-                    tc_wait_ld();
-                    tc_fence_before();
-                    mbar_arrive(smem_u32(&sm.s_free[t]));
-#pragma unroll
-                    for (int e = 64; e < BN; e += 8) {
-                        mxa = fmax3(mxa, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
-                        mxb = fmax3(mxb, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
-                        mxc = fmax3(mxc, __uint_as_float(sr[e + 4]), __uint_as_float(sr[e + 5]));
-                        mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
-                    }
-                } else {
-                if (BN == 128) {
-                    tmem_ld32_into<(BN == 128 ? 64 : 0)>(s_t + 64, sr);
-                    tmem_ld32_into<(BN == 128 ? 96 : 0)>(s_t + 96, sr);
-                }
+                uint32_t sr[CW];
+                tmem_ld_cols(s_t, sr);
                 tc_wait_ld();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sm.s_free[t]));
                 // tile max (raw scores; scale > 0 so max commutes with scaling): four independent chains
-                mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
-                mxd = __uint_as_float(sr[3]);
+                float mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
+                      mxd = __uint_as_float(sr[3]);
 #pragma unroll
-                for (int e = 4; e < BN; e += 8) {
+                for (int e = 4; e < CW; e += 8) {
                     mxa = fmax3(mxa, __uint_as_float(sr[e]), __uint_as_float(sr[e + 1]));
                     mxb = fmax3(mxb, __uint_as_float(sr[e + 2]), __uint_as_float(sr[e + 3]));
-                    if (e + 4 < BN) {
+                    if (e + 4 < CW) {
                         mxc = fmax3(mxc, __uint_as_float(sr[e + 4]), __uint_as_float(sr[e + 5]));
                         mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
                     }
                 }
-                }
-                const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)) * p.scale_log2;
+                const float mx = row_max(fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)), i & 1) * p.scale_log2;
                 bool waited = (i == 0);
                 if (j == 0) {
                     m = mx;
                 } else {
+                    // every thread of a row sees the same mx and m: the RS warps of a lane quarter take the same branch
                     const bool grow = mx > m + RESCALE_THRESHOLD;
                     if (__any_sync(0xffffffffu, grow)) {
                         // rare: O(i-1) must be complete before it is rescaled
@@ -475,119 +466,75 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         waited = true;
                         const float alpha = grow ? exp2f(m - mx) : 1.f;
                         l *= alpha;
+                        if (ch == 0) {   // one warp of the row rescales O; P V (i) waits for every warp's p_ready
 #pragma unroll
-                        for (int c = 0; c < C::NV / 16; ++c) {
-                            uint32_t ov[16];
-                            tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
-                            tc_wait_ld();
+                            for (int c = 0; c < C::NV / 16; ++c) {
+                                uint32_t ov[16];
+                                tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                                tc_wait_ld();
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                            tmem_st_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                                for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                                tmem_st_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                            }
+                            tc_wait_st();
                         }
-                        tc_wait_st();
                         if (grow) m = mx;
                     }
                 }
                 // p = 2^(s*scale - m), kept in registers as packed halves (reusing the score registers) ...
                 const float negm = -m;
-                if (ATTN_LAG == 1 && t == 0) lag_arrive(smem_u32(&sm.lag_bar), __float_as_uint(mx));
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-                const bool sum_here = !p.l_from_o;
-                auto exp_block = [&](auto e_begin, auto e_end) {
+                // HP: packed-half polynomial for part of the pairs (row sums from the ones column: nothing to add up)
+                auto exp_block = [&](auto hp_tag, auto e_begin, auto e_end) {
+                    constexpr bool HP = decltype(hp_tag)::value;
 #pragma unroll
-                for (int e = decltype(e_begin)::value; e < decltype(e_end)::value; e += 2) {
-                    const float x0 = fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm);
-                    const float x1 = fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm);
-                    const float x2 = fmaf(__uint_as_float(sr[2 * e + 2]), p.scale_log2, negm);
-                    const float x3 = fmaf(__uint_as_float(sr[2 * e + 3]), p.scale_log2, negm);
-                    if (C::EXP_F16X2) {
-                        // packed-half exponentials: row sums then come from the ones column / are summed from halves
-                        const uint32_t h01 = ex2_f16x2(cvt_f16x2(x0, x1)), h23 = ex2_f16x2(cvt_f16x2(x2, x3));
-                        if (sum_here) {
-                            const float2 f01 = unpack_half2(h01), f23 = unpack_half2(h23);
-                            l0 += f01.x;
-                            l1 += f01.y;
-                            l2 += f23.x;
-                            l3 += f23.y;
+                    for (int e = decltype(e_begin)::value; e < decltype(e_end)::value; e += 2) {
+                        const float x0 = fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm);
+                        const float x1 = fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm);
+                        const float x2 = fmaf(__uint_as_float(sr[2 * e + 2]), p.scale_log2, negm);
+                        const float x3 = fmaf(__uint_as_float(sr[2 * e + 3]), p.scale_log2, negm);
+                        if constexpr (HP) {
+                            if (hpoly_pair(e, C::HPOLY_OF_8)) sr[e] = ex2_hpoly(x0, x1);
+                            else sr[e] = cvt_f16x2(ex2_f32(x0), ex2_f32(x1));
+                            if (hpoly_pair(e + 1, C::HPOLY_OF_8)) sr[e + 1] = ex2_hpoly(x2, x3);
+                            else sr[e + 1] = cvt_f16x2(ex2_f32(x2), ex2_f32(x3));
+                        } else {
+                            const float p0 = ex2_f32(x0), p1 = ex2_f32(x1), p2 = ex2_f32(x2), p3 = ex2_f32(x3);
+                            l0 += p0;
+                            l1 += p1;
+                            l2 += p2;
+                            l3 += p3;
+                            sr[e] = cvt_f16x2(p0, p1);
+                            sr[e + 1] = cvt_f16x2(p2, p3);
                         }
-                        sr[e] = h01;
-                        sr[e + 1] = h23;
-                        continue;
                     }
-                    // d=40 is exp-bound: POLY_OF_8 of every 8 exponentials run on the FMA pipes instead of the MUFU
-                    const float p0 = ex2_f32(x0);
-                    const float p1 = (C::POLY_OF_8 >= 4 || (C::POLY_OF_8 >= 2 && (e & 2))) ? ex2_poly(x1) : ex2_f32(x1);
-                    const float p2 = ex2_f32(x2);
-                    const float p3 = (C::POLY_OF_8 >= 3 || (C::POLY_OF_8 >= 1 && (e & 2))) ? ex2_poly(x3) : ex2_f32(x3);
-                    if (sum_here) {
-                        l0 += p0;
-                        l1 += p1;
-                        l2 += p2;
-                        l3 += p3;
-                    }
-                    sr[e] = cvt_f16x2(p0, p1);
-                    sr[e + 1] = cvt_f16x2(p2, p3);
-                }
                 };
                 using std::integral_constant;
-                if (ATTN_SPLIT_ST4 && BN == 128) {
-                    const uint32_t pf = smem_u32(&sm.p_free[t]), pf_par = ((uint32_t)(i - 1)) & 1u;
-                    exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 8>{});            // keys 0..31
-                    mbar_wait(pf, pf_par);  // the real wait (i == 0: parity 1 of a fresh barrier passes at once)
-                    tc_fence_after();
-                    tmem_st16_from<0>(p_t, sr);
-                    exp_block(integral_constant<int, BN / 8>{}, integral_constant<int, BN / 4>{});       // keys 32..63
-                    mbar_wait(pf, pf_par);  // completed phase: only a basic-block boundary
-                    tmem_st16_from<(BN == 128 ? 16 : 0)>(p_t + 16, sr);
-                    exp_block(integral_constant<int, BN / 4>{}, integral_constant<int, 3 * BN / 8>{});   // keys 64..95
-                    mbar_wait(pf, pf_par);
-                    tmem_st16_from<(BN == 128 ? 32 : 0)>(p_t + 32, sr);
-                    exp_block(integral_constant<int, 3 * BN / 8>{}, integral_constant<int, BN / 2>{});   // keys 96..127
-                    l += (l0 + l1) + (l2 + l3);
-                    tmem_st16_from<(BN == 128 ? 48 : 0)>(p_t + 48, sr);
-                } else if (ATTN_SPLIT_ST && BN == 128) {
-                    if (pingpong) named_bar_sync(bar_mine, 64);
-                    exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 4>{});   // keys 0..63
+                // ... in two pieces: the first half of the packed probabilities is stored (tcgen05.st) after half of the
+                // exponentials; the p_free spin in between also splits the basic block, so ptxas cannot sink all packs
+                // behind the last ex2 (r1o: +10 %).  The wait for P(i-1) to be consumed by its P V product overlaps the
+                // first half of the exponentials.
+                auto two_pieces = [&](auto hp_tag) {
+                    exp_block(hp_tag, integral_constant<int, 0>{}, integral_constant<int, CW / 4>{});
                     if (!waited) {
                         mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
                         tc_fence_after();
                     }
-                    tmem_st32_from<0>(p_t, sr);                                                   // packed pairs 0..31
-                    exp_block(integral_constant<int, BN / 4>{}, integral_constant<int, BN / 2>{});  // keys 64..127
-                    // hand the MUFU to the paired warp (slot 1 keeps the token after its very last tile: slot 0 is done)
-                    if (pingpong && !(t == 1 && i == T - 1)) named_bar_arrive(bar_other, 64);
-                    l += (l0 + l1) + (l2 + l3);
-                    tmem_st32_from<(BN == 128 ? 32 : 0)>(p_t + 32, sr);
-                } else if (ATTN_SPLIT_ST && BN == 64) {
-                    if (pingpong) named_bar_sync(bar_mine, 64);
-                    exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 4>{});   // keys 0..31
-                    if (!waited) {
-                        mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
-                        tc_fence_after();
-                    }
-                    tmem_st16_from<0>(p_t, sr);                                                   // packed pairs 0..15
-                    exp_block(integral_constant<int, BN / 4>{}, integral_constant<int, BN / 2>{});  // keys 32..63
-                    if (pingpong && !(t == 1 && i == T - 1)) named_bar_arrive(bar_other, 64);
-                    l += (l0 + l1) + (l2 + l3);
-                    tmem_st16_from<(BN == 64 ? 16 : 0)>(p_t + 16, sr);
+                    tmem_st_packed<0, CW / 4>(p_t, sr);
+                    exp_block(hp_tag, integral_constant<int, CW / 4>{}, integral_constant<int, CW / 2>{});
+                    tmem_st_packed<CW / 4, CW / 4>(p_t + CW / 4, sr);
+                };
+                if (C::HPOLY_OF_8 > 0 && p.l_from_o) {
+                    two_pieces(std::true_type{});
                 } else {
-                exp_block(integral_constant<int, 0>{}, integral_constant<int, BN / 2>{});
-                if (ATTN_LAG == 2 && t == 0) lag_arrive(smem_u32(&sm.lag_bar), sr[BN / 4 - 1]);
-                l += (l0 + l1) + (l2 + l3);
-                // ... so that the wait for P(i-1) to be consumed by its P V product overlaps the exponentials
-                if (!waited) {
-                    mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
-                    tc_fence_after();
-                }
-                // A operand of P V in TMEM: lane = query row, column e = keys (2e, 2e+1) packed
-                tmem_st32_from<0>(p_t, sr);
-                if (BN == 128) tmem_st32_from<(BN == 128 ? 32 : 0)>(p_t + 32, sr);
+                    two_pieces(std::false_type{});
+                    l += (l0 + l1) + (l2 + l3);
                 }
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sm.p_ready[t]));
             }
-            // ---- end of source: acc += w_s * O / l
+            // ---- end of source: acc += w_s * O / l  (the 16-column chunks of O are dealt to the RS threads of the row)
             const int ilast = s * nkt + nkt - 1;
             mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)ilast) & 1u);
             tc_fence_after();
@@ -596,10 +543,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 tmem_ld_32x32b_x16(o_t + (uint32_t)(D / 16 * 16), lv);  // the 16-column chunk that holds column D
                 tc_wait_ld();
                 l = __uint_as_float(lv[D % 16]);
+            } else {
+                l = row_sum(l, s & 1);
             }
             const float wl = p.weight[s] / l;
 #pragma unroll
             for (int c = 0; c < C::NV / 16; ++c) {
+                if (c % RS != ch) continue;
                 uint32_t ov[16], av[16];
                 tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
                 if (C::ACC_IN_TMEM && s > 0) tmem_ld_32x32b_x16(acc_t + (uint32_t)(c * 16), av);
@@ -619,11 +569,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tc_fence_before();
             mbar_arrive(smem_u32(&sm.o_free[t]));
         }
-        // ---- store the row: D halves = D/8 x 16 B
+        // ---- store the row: D halves = D/8 x 16 B; every thread stores the chunks it accumulated itself
         const long long grow_ = (long long)b * p.Nq + (qt * NSLOT + t) * BM + row;
         uint4* dst = reinterpret_cast<uint4*>(p.out + grow_ * p.ld_out + head * D);
 #pragma unroll
         for (int c = 0; c < (D + 15) / 16; ++c) {
+            if (c % RS != ch) continue;
             float o16[16];
             if (C::ACC_IN_TMEM) {
                 uint32_t av[16];
@@ -690,7 +641,7 @@ int launch(const void* q, int ld_q, const void* k, const void* v, int ld_kv, con
         GCB_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     dim3 grid((Nq / BM + C::NSLOT - 1) / C::NSLOT, heads, B);
-    attn_tc_kernel<D_><<<grid, 32 * (4 * C::NSLOT + 2), smem, stream>>>(tmQ, tmK, tmV, tmK2, tmV2, p);
+    attn_tc_kernel<D_><<<grid, attn_threads<D_>(), smem, stream>>>(tmQ, tmK, tmV, tmK2, tmV2, p);
     GCB_LAUNCH_CHECK();
     return GCB_OK;
 }

@@ -190,7 +190,10 @@ class SD15Denoiser:
         self.cnet = PackedNet(cnet_sd, self.dev, heads)
         self.heads = heads
         self.fuse_geglu = fuse_geglu
-        self.ones_column = False
+        # head dim 40: V heads padded to 48 columns with a ones column, so the softmax row sums come out of the P V
+        # product and the attention kernel may evaluate part of its exponentials as packed-half polynomials
+        # (attn_tc.cu ex2_hpoly: 530 -> 620-634 TFLOP/s on B200, profiles/r3_attn.md)
+        self.ones_column = True
         self.ch = [unet_sd[f"down_blocks.{i}.resnets.0.conv1.weight"].shape[0] for i in range(4)]
         self._temb_layout: Dict[int, Tuple[List[str], Dict[str, int], int]] = {}
         self.text_kv: Dict[Tuple[int, str, int], torch.Tensor] = {}
@@ -277,14 +280,13 @@ class SD15Denoiser:
         n1 = ops.layernorm(h, net.vec(blk + ".norm1.weight"), net.vec(blk + ".norm1.bias"))
         if d == 40 and self.ones_column:
             # head dim 40: V heads padded to 48 columns with a ones column -> row sums come out of the P V product
-            # (measured on B200: no gain over summing in the softmax threads - the kernel is MUFU-bound - so off by default)
-            wqkv, bqkv = net.qkv_ones_padded(blk + ".attn1", heads, 48)
-            qkv = ops.linear(n1, wqkv, bqkv)  # [B,N,2C+heads*48]
+            wqkv, bqkv = net.qkv_ones_padded(blk + ".attn1", heads, 48)   # [2C + heads*48, C]
             ld, vstride = 2 * C + heads * 48, 48
         else:
             wqkv, _ = net.cat_lin([blk + ".attn1.to_q", blk + ".attn1.to_k", blk + ".attn1.to_v"])
-            qkv = None
+            bqkv = None
             ld, vstride = 3 * C, d
+        qkv = None
         layer = f"{net_id}:{blk}.attn1"
         kv2 = None
         if plan.gather is not None:
@@ -293,19 +295,19 @@ class SD15Denoiser:
             if qkv is None and _FUSED_GATHER and hasattr(plan.gather, "linear_gather"):
                 # one kernel: the GEMM's epilogue stores every output tile into all ranks' K/V buffers over NVLink
                 # (gcb_linear_allgather_fwd); the local rows are read back out of the gathered buffer
-                fused = plan.gather.linear_gather(layer, n1, wqkv, None, C)   # the Q third (C columns) stays local
+                fused = plan.gather.linear_gather(layer, n1, wqkv, bqkv, C)   # the Q third (C columns) stays local
             if fused is not None:
                 kv2, qkv = fused
                 ops.LAUNCHES[0] += 2
             else:
                 if qkv is None:
-                    qkv = ops.linear(n1, wqkv)  # [B,N,3C]
+                    qkv = ops.linear(n1, wqkv, bqkv)  # [B,N,ld]
                 kv2 = plan.gather(layer, qkv)   # GEMM, then push + flag kernels (or NCCL)
             if plan.record_kv is not None:
                 plan.record_kv[layer] = kv2
         else:
             if qkv is None:
-                qkv = ops.linear(n1, wqkv)  # [B,N,3C]
+                qkv = ops.linear(n1, wqkv, bqkv)  # [B,N,ld]
             if plan.record_kv is not None:
                 plan.record_kv[layer] = qkv
             kv2 = plan.ref_kv[layer] if plan.ref_kv is not None else None
