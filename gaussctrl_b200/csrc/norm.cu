@@ -80,60 +80,87 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __re
     }
 }
 
+// y = act(x * a[c] + b[c]) with a = rstd * gamma, b = beta - mean * a.
+// Prologue: eight threads per group add up the chunk partials (fixed order: deterministic, independent of the batch).
+// Body: thread (pixel lane ty, channel vector tx) keeps the a/b of its 8 channels in REGISTERS and walks the CTA's
+// pixels ty, ty + L, ... with 16-byte coalesced loads and stores - no shared-memory reads and no integer division
+// per element (round 2: 2 LDS per value + one division per 16 bytes held the kernel at 2.8 TB/s).
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2,
                                                        const __half* __restrict__ gamma, const __half* __restrict__ beta,
                                                        const float* __restrict__ partial, __half* __restrict__ y, int HW,
                                                        int C1, int C2, int groups, int nchunks, int pix_per_cta,
                                                        float eps, int silu) {
-    extern __shared__ float s_ab[];  // a[C], b[C]
     __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
     const int b = blockIdx.y, tid = threadIdx.x;
     const int C = C1 + C2, cpg = C / groups;
-    if (tid < groups) {
+    {
+        const int g = tid >> 3, part = tid & 7;
         float sum = 0.f, sq = 0.f;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const float* pp = partial + (((long long)b * nchunks + ch) * groups + tid) * 2;
-            sum += pp[0];
-            sq += pp[1];
+        if (g < groups) {
+#pragma unroll 4
+            for (int ch = part; ch < nchunks; ch += 8) {
+                const float2 pp = *reinterpret_cast<const float2*>(partial + (((long long)b * nchunks + ch) * groups + g) * 2);
+                sum += pp.x;
+                sq += pp.y;
+            }
         }
-        const float n = (float)HW * (float)cpg;
-        const float mean = sum / n;
-        const float var = fmaxf(sq / n - mean * mean, 0.f);
-        s_mean[tid] = mean;
-        s_rstd[tid] = rsqrtf(var + eps);
-    }
-    __syncthreads();
-    float* sa = s_ab;
-    float* sb = s_ab + C;
-    for (int c = tid; c < C; c += 256) {
-        const int g = c / cpg;
-        const float a = s_rstd[g] * __half2float(gamma[c]);
-        sa[c] = a;
-        sb[c] = __half2float(beta[c]) - s_mean[g] * a;
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+        if (g < groups && part == 0) {
+            const float n = (float)HW * (float)cpg;
+            const float mean = sum / n;
+            const float var = fmaxf(sq / n - mean * mean, 0.f);
+            s_mean[g] = mean;
+            s_rstd[g] = rsqrtf(var + eps);
+        }
     }
     __syncthreads();
     const int cv = C / 8;
+    const int cvb = cv < 256 ? cv : 256;   // channel vectors per pass (C = 2560: two passes)
+    const int nl = 256 / cvb;              // pixel lanes
+    const int tx = tid % cvb, ty = tid / cvb;
+    if (ty >= nl) return;
     const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
-    const long long total = (long long)(p1 - p0) * cv;
-    for (long long i = tid; i < total; i += 256) {
-        const int v = (int)(i % cv);
-        const long long pix = (long long)b * HW + p0 + i / cv;
+    for (int v = tx; v < cv; v += cvb) {
         const int c = v * 8;
-        const uint4 raw = *reinterpret_cast<const uint4*>(gn_src(x1, x2, C1, C2, pix, c));
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        uint32_t o[4];
+        float a[8], bb[8];
+        {
+            const uint4 gr = *reinterpret_cast<const uint4*>(gamma + c), br = *reinterpret_cast<const uint4*>(beta + c);
+            const uint32_t gw[4] = {gr.x, gr.y, gr.z, gr.w}, bw[4] = {br.x, br.y, br.z, br.w};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_half2(w[t]);
-            float r0 = f.x * sa[c + 2 * t] + sb[c + 2 * t];
-            float r1 = f.y * sa[c + 2 * t + 1] + sb[c + 2 * t + 1];
-            if (silu) {
-                r0 = silu_f(r0);
-                r1 = silu_f(r1);
+            for (int t = 0; t < 4; ++t) {
+                const float2 gf = unpack_half2(gw[t]), bf = unpack_half2(bw[t]);
+                const int g0 = (c + 2 * t) / cpg;   // groups own whole channel pairs
+                a[2 * t] = s_rstd[g0] * gf.x;
+                a[2 * t + 1] = s_rstd[g0] * gf.y;
+                bb[2 * t] = bf.x - s_mean[g0] * a[2 * t];
+                bb[2 * t + 1] = bf.y - s_mean[g0] * a[2 * t + 1];
             }
-            o[t] = pack_half2(r0, r1);
         }
-        *reinterpret_cast<uint4*>(y + pix * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+        const __half* src = c < C1 ? x1 + ((long long)b * HW) * C1 + c : x2 + ((long long)b * HW) * C2 + (c - C1);
+        const int ld = c < C1 ? C1 : C2;
+        __half* dst = y + ((long long)b * HW) * C + c;
+#pragma unroll 4
+        for (int pix = p0 + ty; pix < p1; pix += nl) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(src + (long long)pix * ld);
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_half2(w[t]);
+                float r0 = f.x * a[2 * t] + bb[2 * t];
+                float r1 = f.y * a[2 * t + 1] + bb[2 * t + 1];
+                if (silu) {
+                    r0 = silu_f(r0);
+                    r1 = silu_f(r1);
+                }
+                o[t] = pack_half2(r0, r1);
+            }
+            *reinterpret_cast<uint4*>(dst + (long long)pix * C) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
@@ -222,15 +249,72 @@ extern "C" int gcb_groupnorm_nhwc_fwd(const void* x1, const void* x2, const void
     gn_stats_kernel<<<dim3(nchunks, B), GN_THREADS, 0, st>>>((const __half*)x1, (const __half*)x2, (float*)workspace, HW, C1,
                                                       C2, groups, ppc);
     GCB_LAUNCH_CHECK();
-    // apply: ~64 pixels per CTA at C>=1280, more for narrow tensors
-    int pix_per_cta = 16384 / C;
+    // apply: 64 KB of the tensor per CTA
+    int pix_per_cta = 32768 / C;
     if (pix_per_cta < 8) pix_per_cta = 8;
-    const size_t smem = (size_t)C * 2 * sizeof(float);
-    gn_apply_kernel<<<dim3(gcb_cdiv(HW, pix_per_cta), B), 256, smem, st>>>(
+    gn_apply_kernel<<<dim3(gcb_cdiv(HW, pix_per_cta), B), 256, 0, st>>>(
         (const __half*)x1, (const __half*)x2, (const __half*)gamma, (const __half*)beta, (const float*)workspace,
         (__half*)y, HW, C1, C2, groups, nchunks, pix_per_cta, eps, silu);
     GCB_LAUNCH_CHECK();
     return GCB_OK;
+}
+
+// C = 40 L (320: L = 8, 640: L = 16): L lanes per row, five 16-byte vectors per lane, 32 / L rows per warp - every lane
+// carries the same load (one warp per 640-byte row left 24 lanes with a single vector: 3.7 TB/s at C = 320).
+template <int L>
+__global__ void __launch_bounds__(256) layernorm5_kernel(const __half* __restrict__ x, const __half* __restrict__ gamma,
+                                                         const __half* __restrict__ beta, __half* __restrict__ y, int M,
+                                                         float eps) {
+    constexpr int C = 40 * L, RPW = 32 / L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / L, j = lane % L;
+    const long long row = ((long long)blockIdx.x * 8 + warp) * RPW + sub;
+    const bool ok = row < M;
+    uint4 raw[5];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        raw[i] = ok ? *reinterpret_cast<const uint4*>(x + row * C + (j + i * L) * 8) : make_uint4(0, 0, 0, 0);
+        const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_half2(w[t]);
+            sum += f.x + f.y;
+        }
+    }
+#pragma unroll
+    for (int o = L / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_half2(w[t]);
+            sq += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        }
+    }
+#pragma unroll
+    for (int o = L / 2; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+    if (!ok) return;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int v = j + i * L;
+        const uint4 gr = *reinterpret_cast<const uint4*>(gamma + v * 8);
+        const uint4 br = *reinterpret_cast<const uint4*>(beta + v * 8);
+        const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+        const uint32_t gw[4] = {gr.x, gr.y, gr.z, gr.w};
+        const uint32_t bw[4] = {br.x, br.y, br.z, br.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_half2(w[t]), g = unpack_half2(gw[t]), b = unpack_half2(bw[t]);
+            o[t] = pack_half2((f.x - mean) * rstd * g.x + b.x, (f.y - mean) * rstd * g.y + b.y);
+        }
+        *reinterpret_cast<uint4*>(y + row * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
 }
 
 extern "C" int gcb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int M, int C, float eps,
@@ -239,7 +323,13 @@ extern "C" int gcb_layernorm_fwd(const void* x, const void* gamma, const void* b
     GCB_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * 8, "LayerNorm C=%d unsupported (multiple of 8, <= 2048)", C);
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = gcb_cdiv(M, 8);
-    if (C <= 512)
+    if (C == 320) {
+        layernorm5_kernel<8><<<gcb_cdiv(M, 32), 256, 0, st>>>((const __half*)x, (const __half*)gamma, (const __half*)beta,
+                                                              (__half*)y, M, eps);
+    } else if (C == 640) {
+        layernorm5_kernel<16><<<gcb_cdiv(M, 16), 256, 0, st>>>((const __half*)x, (const __half*)gamma, (const __half*)beta,
+                                                               (__half*)y, M, eps);
+    } else if (C <= 512)
         layernorm_kernel<2><<<blocks, 256, 0, st>>>((const __half*)x, (const __half*)gamma, (const __half*)beta,
                                                     (__half*)y, M, C, eps);
     else if (C <= 1280)
