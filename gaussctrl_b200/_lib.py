@@ -28,6 +28,7 @@ SIGNATURES = {
     "gcb_conv2d_nhwc_fwd": (c_int, [_P, _P, _P, _P, c_int, _P, _P] + [c_int] * 8 + [_P]),
     "gcb_conv2d_direct_nhwc_fwd": (c_int, [_P, _P, _P, _P, _P] + [c_int] * 10 + [_P]),
     "gcb_im2col3x3_s2_nhwc": (c_int, [_P, _P] + [c_int] * 6 + [_P]),
+    "gcb_im2col3x3_c4_nhwc": (c_int, [_P, _P] + [c_int] * 3 + [_P]),
     "gcb_geglu_tile_n": (c_int, [c_int]),
     "gcb_geglu_pack_rows": (c_int, [c_int, _IP]),
     "gcb_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),

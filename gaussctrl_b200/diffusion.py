@@ -125,6 +125,17 @@ class PackedNet:
             self._cache[key] = (wp, bp)
         return self._cache[key]
 
+    def conv_c4(self, name: str):
+        """3x3 conv over 4 input channels as a K = 40 GEMM (ops.conv3x3_c4) -> (w [Cout, 40], bias)"""
+        key = "convc4:" + name
+        if key not in self._cache:
+            w, b, _ = self.conv(name)
+            assert w.shape[1] == 36, w.shape
+            wp = torch.zeros((w.shape[0], 40), dtype=torch.float16, device=self.dev)
+            wp[:, :36] = w
+            self._cache[key] = (wp, b)
+        return self._cache[key]
+
     def conv_split(self, name: str, c1: int):
         """1x1 conv over a channel concat, split into the two K ranges -> (w1, w2, bias)"""
         key = "convsplit:" + name
@@ -362,13 +373,14 @@ class SD15Denoiser:
         cn, un = self.cnet, self.unet
         # ---- ControlNet
         tp_c = self._temb(cn, 1, t_dev)
-        w, b, _ = cn.conv("conv_in")
-        xc = ops.conv2d_direct(x, w, b, 3, 1, (1, 1), GCB_ACT_NONE, residual=cond_emb)
+        col = ops.im2col3x3_c4(x)   # the 3x3 patches of the latents, shared by both conv_in
+        w, b = cn.conv_c4("conv_in")
+        xc = ops.conv3x3_c4(x, w, b, residual=cond_emb, col=col)
         c_mid, c_skips = self._encoder(cn, 1, xc, tp_c, plan)
         # ---- UNet down + mid
         tp_u = self._temb(un, 0, t_dev)
-        w, b, _ = un.conv("conv_in")
-        xu = ops.conv2d_direct(x, w, b, 3, 1, (1, 1), GCB_ACT_NONE)
+        w, b = un.conv_c4("conv_in")
+        xu = ops.conv3x3_c4(x, w, b, col=col)
         u_mid, u_skips = self._encoder(un, 0, xu, tp_u, plan)
         # ---- add the ControlNet residuals: zero-conv GEMM with the UNet tensor as residual epilogue
         skips = []

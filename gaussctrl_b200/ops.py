@@ -106,6 +106,29 @@ def conv3x3_s2(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], p
     return y.reshape(B, Ho, Wo, w.shape[0])
 
 
+def im2col3x3_c4(x: torch.Tensor) -> torch.Tensor:
+    """x [B,H,W,4] fp16 -> 3x3 / stride 1 / pad 1 patches [1,1,B*H*W,40] ((kh,kw,c) order, 4 zero columns)."""
+    B, H, W, C = x.shape
+    assert C == 4, x.shape
+    col = torch.empty((1, 1, B * H * W, 40), dtype=torch.float16, device=x.device)
+    check(lib.gcb_im2col3x3_c4_nhwc(_p(_f16(x)), _p(col), B, H, W, _stream()))
+    LAUNCHES[0] += 1
+    return col
+
+
+def conv3x3_c4(x: torch.Tensor, w40: torch.Tensor, bias: Optional[torch.Tensor],
+               residual: Optional[torch.Tensor] = None, col: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution of a 4-channel tensor (conv_in on the latents) as a K = 40 GEMM on the tensor
+    cores over its patches (`col` = im2col3x3_c4(x), shared by the UNet's and the ControlNet's conv_in).
+    w40 [Cout, 40] = the OHWI weights [Cout, 36] zero-padded."""
+    B, H, W, _ = x.shape
+    assert w40.shape[1] == 40, w40.shape
+    if col is None:
+        col = im2col3x3_c4(x)
+    y = conv2d(col, w40, bias, 1, residual=None if residual is None else residual.reshape(1, 1, B * H * W, -1))
+    return y.reshape(B, H, W, w40.shape[0])
+
+
 def geglu_perm(cout: int, device) -> torch.Tensor:
     perm = (ctypes.c_int32 * cout)()
     check(lib.gcb_geglu_pack_rows(cout, perm))

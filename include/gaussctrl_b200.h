@@ -72,6 +72,9 @@ int gcb_conv2d_direct_nhwc_fwd(const void* x, const void* w, const void* bias, c
 
 /* im2col for 3x3 stride-2 convolutions (Downsample2D): x [B,H,W,C] -> col [B*Ho*Wo, 9*C]. */
 int gcb_im2col3x3_s2_nhwc(const void* x, void* col, int B, int H, int W, int C, int pad_lo, int pad_hi, void* stream);
+/* 3x3 / stride 1 / pad 1 patches of a 4-channel tensor x [B,H,W,4] -> col [B*H*W, 40] fp16 ((kh,kw,c) order, columns
+ * 36..39 zero): conv_in of UNet2DConditionModel / ControlNetModel (latents, 4 channels) as a K = 40 tensor-core GEMM. */
+int gcb_im2col3x3_c4_nhwc(const void* x, void* col, int B, int H, int W, void* stream);
 
 /* Row permutation that turns a diffusers GEGLU projection [8C, C] into the tile-interleaved layout
  * GCB_ACT_GEGLU expects.  h_perm (host, int32[Cout]) receives source-row indices; tile_n is the N tile used. */

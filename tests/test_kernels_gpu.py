@@ -205,6 +205,26 @@ def test_geglu_fused(ops, C):
     assert rel < 3e-3, (rel, mx)
 
 
+def test_conv_in_as_gemm(ops):
+    """conv_in on the latents (4 channels): patches [M, 40] + a K = 40 GEMM (K not a multiple of the 64-column TMA box:
+    the box is zero-filled beyond column 40) == the direct convolution == fp32 torch."""
+    B, H, W, Cout = 3, 64, 64, 320
+    x = _rand((B, H, W, 4), 31)
+    w = _rand((Cout, 36), 32, scale=1.0 / 6)
+    b = _rand((Cout,), 33)
+    res = _rand((B, H, W, Cout), 34)
+    w40 = torch.zeros((Cout, 40), dtype=torch.float16, device="cuda")
+    w40[:, :36] = w
+    y = ops.conv3x3_c4(x, w40, b, residual=res)
+    ref = _conv_ref(x, w, b, 3, residual=res)
+    rel, mx = _relerr(y, ref)
+    assert rel < 2e-3, (rel, mx)
+    y2 = ops.conv2d_direct(x, w, b, 3, 1, (1, 1), 0, residual=res)
+    assert _relerr(y, y2)[0] < 2e-3
+    # batch invariance of the patch + GEMM path
+    assert torch.equal(y[:1], ops.conv3x3_c4(x[:1].contiguous(), w40, b, residual=res[:1].contiguous()))
+
+
 def test_direct_conv_and_im2col(ops):
     x = _rand((2, 16, 16, 4), 1)
     w = _rand((320, 9 * 4), 2, scale=0.2)
