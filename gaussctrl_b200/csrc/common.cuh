@@ -86,18 +86,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // x * sigmoid(x).  x -> -large: ex2 -> inf, rcp -> 0, result -0 (the limit); x -> +large: ex2 -> 0, result x.
 __device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
 // exact (erf) GELU, x * Phi(x), with erfc from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output
-// rounding): ~17 instructions (2 MUFU) instead of erff's ~30 - the GEGLU GEMM epilogue is issue-bound on this function.
-// The negative branch uses erfc directly (no 1 - (1 - e) cancellation).
-__device__ __forceinline__ float gelu_erf_f(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = p * t * ex2_approx(z * z * -1.4426950408889634f);  // erfc(z), z >= 0
-    return 0.5f * x * (x >= 0.f ? 2.f - e : e);
+// rounding).  The GEGLU GEMM epilogue is issue-bound on this function (profiles/r3p_gemm_geglu320_source_summary.txt),
+// so every constant is folded: with z = |x| / sqrt(2),
+//   t = 1 / (1 + 0.3275911 z) = rcp(fma(|x|, 0.23164189, 1)),   exp(-z^2) = ex2(x^2 * -0.72134752),
+//   h = erfc(z) / 2 = (poly(t) / 2) * t * exp(-z^2)             (coefficients pre-halved),
+//   Phi(x) = x >= 0 ? 1 - h : h   (the negative branch uses erfc directly: no 1 - (1 - e) cancellation)
+// 14 FMA-pipe instructions + 2 MUFU (round 2: 21 + 2; erff: ~30).  gelu_erf_phi returns Phi(x) alone so that a caller
+// multiplying by something else anyway (GEGLU: value * gate * Phi(gate)) spends one product less.
+__device__ __forceinline__ float gelu_erf_phi(float x) {
+    const float t = rcp_approx(fmaf(fabsf(x), 0.23164189f, 1.f));
+    float p = fmaf(0.5307027145f, t, -0.7265760135f);
+    p = fmaf(p, t, 0.7107068705f);
+    p = fmaf(p, t, -0.142248368f);
+    p = fmaf(p, t, 0.127414796f);
+    const float h = p * t * ex2_approx(x * x * -0.72134752044448170f);  // erfc(|x| / sqrt 2) / 2
+    return x >= 0.f ? 1.f - h : h;
 }
+__device__ __forceinline__ float gelu_erf_f(float x) { return x * gelu_erf_phi(x); }
 
 // ---- warp-uniform role dispatch --------------------------------------------------------------------------------
 // The warp index is broadcast with a shuffle so the compiler can prove the role branches warp-uniform, and the single

@@ -437,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     add8(gate + 8, bgp[1]);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = val[j] * gelu_erf_f(gate[j]);
+                for (int j = 0; j < 16; ++j) o[j] = (val[j] * gate[j]) * gelu_erf_phi(gate[j]);
                 const uint32_t h0 = pack_half2(o[0], o[1]), h1 = pack_half2(o[2], o[3]), h2 = pack_half2(o[4], o[5]),
                                h3 = pack_half2(o[6], o[7]), h4 = pack_half2(o[8], o[9]), h5 = pack_half2(o[10], o[11]),
                                h6 = pack_half2(o[12], o[13]), h7 = pack_half2(o[14], o[15]);

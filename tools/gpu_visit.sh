@@ -4,7 +4,8 @@
 #   bench  <tag> [bench args]  bench.py on one GPU
 #   multi  <N> <tag> [args]    bench.py under torchrun on N GPUs (+ the 2-GPU pytest when N >= 2 and tag ends in "t")
 #   profile <tag>              ncu launch list of one eager denoise step (view batch 36) + ncu --set full of the attention
-#                              kernel at B = 72 rows + warm launch list of two eval renders
+#                              kernel at B = 72 rows + ncu --set full of the persistent GEMM (GEGLU 320 -> 2560)
+#                              + warm launch list of two eval renders
 set -x
 mkdir -p gpurun_out
 what=$1; shift
@@ -29,6 +30,9 @@ case $what in
     GCB_PROFILE_BQ=72 timeout 900 ncu --set full --import-source on --clock-control none -k regex:attn_tc_kernel -s 1 -c 1 \
       -o gpurun_out/${tag}_attn_b72 -f python tools/profile_attn.py 3 > gpurun_out/${tag}_attn.log 2>&1
     ncu -i gpurun_out/${tag}_attn_b72.ncu-rep --page details > gpurun_out/${tag}_attn_b72_ncu.txt 2>&1
+    timeout 600 ncu --set full --import-source on --clock-control none -k regex:gemm_tc_kernel -s 2 -c 1 \
+      -o gpurun_out/${tag}_gemm_geglu320 -f python tools/profile_gemm.py > gpurun_out/${tag}_gemm.log 2>&1
+    ncu -i gpurun_out/${tag}_gemm_geglu320.ncu-rep --page details > gpurun_out/${tag}_gemm_geglu320_ncu.txt 2>&1
     timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
       --cache-control none -c 45 --csv --log-file gpurun_out/${tag}_raster_launches.csv python tools/time_raster.py 1000000 2 \
       > gpurun_out/${tag}_raster.log 2>&1 ;;
