@@ -58,11 +58,26 @@ struct Cfg<40> {
 #endif
     // key pairs out of every 8 whose exponentials run as ONE packed-half polynomial on the FMA / ALU pipes (ex2_hpoly)
     // instead of two MUFU.EX2 + one F2FP; only when the row sums come out of the P V product (V ones column).
-    // 2 / 3 / 4 of 8 measure the same (628 / 623 / 617 TFLOP/s, r3h), 5 of 8: 575, 6 of 8: 480 (HFMA2 issues at half rate)
+    // 2 / 3 / 4 of 8 measure the same (628 / 623 / 617 TFLOP/s, r3h; with the shift in the MMA 673 / 662 / 674, r3s), 5 of
+    // 8: 575, 6 of 8: 480 (HFMA2 issues at half rate).  2 of 8 = the fewest instructions of the three.
 #ifdef GCB_ATTN_HPOLY
     static constexpr int HPOLY_OF_8 = GCB_ATTN_HPOLY;
 #else
-    static constexpr int HPOLY_OF_8 = 3;
+    static constexpr int HPOLY_OF_8 = 2;
+#endif
+    // The scale and the running reference m are folded into the Q K^T product: Q is multiplied by scale * log2(e) once
+    // per CTA (in shared memory), and a fourth k-step multiplies Q's columns 48..63 - column 48 holds -m of the row, an
+    // fp16-exact value - with a constant tile whose column 48 is 1.0.  S then arrives in TMEM as s * scale - m: the 128
+    // FFMAs per row and tile that applied scale and shift (a fifth of the softmax warps' instructions) disappear.  m
+    // changes only at the first tile of a source or when a tile's maximum exceeds it by 2^8 (the lazy-rescale rule):
+    // the thread then shifts that tile's scores itself, rewrites its -m in shared memory and only afterwards releases S
+    // for the next Q K^T.  633 -> 662-674 TFLOP/s (profiles/r3s_ab_attn_shift.txt).  The tile at which m moves runs a second
+    // copy of the exponential code that subtracts the difference (modifying the 128 score registers in place in a rare
+    // branch made ptxas spill ~25 of them on EVERY tile: 425 TFLOP/s, r3r).
+#if defined(GCB_ATTN_NO_SHIFT_MMA)
+    static constexpr bool SHIFT_IN_MMA = false;
+#else
+    static constexpr bool SHIFT_IN_MMA = ROWSPLIT == 1;
 #endif
 };
 template <>
@@ -70,6 +85,7 @@ struct Cfg<80> {
     static constexpr int D = 80, BN = 64, DK = 80, NV = 80, BOXES = 2, NSLOT = 2, STAGES = 4;
     static constexpr bool ZERO_Q_PAD = false, ACC_IN_TMEM = true;
     static constexpr int ROWSPLIT = 1, HPOLY_OF_8 = 0;
+    static constexpr bool SHIFT_IN_MMA = false;
     static constexpr uint32_t TM_S = 0, TM_O = 128, TM_O_STRIDE = 80, TM_P = 288, TM_ACC = 352;
 };
 
@@ -94,6 +110,7 @@ struct __align__(1024) Smem {
     uint8_t q[NSLOT][C::BOXES][QBOX];
     uint8_t k[STAGES][C::BOXES][KVBOX];
     uint8_t v[STAGES][C::BOXES][KVBOX];
+    uint8_t ones[C::SHIFT_IN_MMA ? KVBOX : 1024];   // K-box-shaped constant tile: column 48 = 1.0, columns 49..63 = 0
     float acc[C::ACC_IN_TMEM ? 1 : NSLOT][C::ACC_IN_TMEM ? 1 : C::D][C::ACC_IN_TMEM ? 4 : BM];  // [slot][column][row]
     // row split: the tile max (by tile parity) and the row sum (by source parity) of each thread of a row
     float xmax[RS > 1 ? NSLOT : 1][2][RS > 1 ? RS : 1][RS > 1 ? BM : 4];
@@ -235,7 +252,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     constexpr int D = C::D, BN = C::BN, BOXES = C::BOXES, NSLOT = C::NSLOT, STAGES = C::STAGES, RS = C::ROWSPLIT;
     constexpr int NSW = 4 * RS;                       // softmax warps per slot
     constexpr int W_TMA = NSW * NSLOT, W_MMA = NSW * NSLOT + 1;
-    constexpr int KSTEPS = C::DK / 16, PV_STEPS = BN / 16, PCOLS = BN / 2;
+    constexpr int KSTEPS = C::DK / 16 + (C::SHIFT_IN_MMA ? 1 : 0), PV_STEPS = BN / 16, PCOLS = BN / 2;
+    static_assert(!C::SHIFT_IN_MMA || (C::DK == 48 && BN == BM && RS == 1), "shift step = k-step 3 of the first 64-column box");
     constexpr int CW = BN / RS;                       // score columns (keys) of a tile per softmax thread
     constexpr uint32_t STAGE_BYTES = BOXES * SM::KVBOX;
     constexpr uint32_t SLOT_THREADS = 32 * NSW;
@@ -336,7 +354,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                     // 16 halves = 32 B per k-step inside a 64-column box (4 k-steps per box)
                     const uint64_t qd = make_smem_desc(smem_u32(sm.q[t][ks >> 2]) + (uint32_t)((ks & 3) * 32), 16, 1024, 2);
-                    const uint64_t kd = make_smem_desc(smem_u32(sm.k[st][ks >> 2]) + (uint32_t)((ks & 3) * 32), 16, 1024, 2);
+                    // the shift step (ks == 3) multiplies Q's columns 48..63 with the constant tile instead of K
+                    const uint32_t kbox = (C::SHIFT_IN_MMA && ks == KSTEPS - 1) ? smem_u32(sm.ones) : smem_u32(sm.k[st][ks >> 2]);
+                    const uint64_t kd = make_smem_desc(kbox + (uint32_t)((ks & 3) * 32), 16, 1024, 2);
                     tc_mma_ss(tmem + C::TM_S + (uint32_t)(t * BN), qd, kd, idesc_qk, (uint32_t)(ks != 0));
                 }
                 tc_commit(smem_u32(&sm.s_full[t]));
@@ -399,10 +419,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // named barrier of the RS warps that share this slot's TMEM lane quarter (ids 1 .. 4 NSLOT)
         const uint32_t pair_bar = 1u + (uint32_t)(t * 4 + wq);
         mbar_wait(smem_u32(&sm.q_full), 0);
-        if (C::ZERO_Q_PAD && ch == 0) {
-            // zero Q columns 40..47: 16-byte chunk 5 of the 128B-swizzled row
-            uint8_t* qrow = sm.q[t][0] + (row >> 3) * 1024 + (row & 7) * 128 + ((5 ^ (row & 7)) * 16);
-            *reinterpret_cast<uint4*>(qrow) = make_uint4(0, 0, 0, 0);
+        // this thread's Q row in the 128B-swizzled box: 16-byte chunk j at (j ^ (row & 7)) * 16
+        uint8_t* const qrow = sm.q[t][0] + (row >> 3) * 1024 + (row & 7) * 128;
+        auto qchunk = [&](int j) { return reinterpret_cast<uint4*>(qrow + ((j ^ (row & 7)) * 16)); };
+        if constexpr (C::SHIFT_IN_MMA) {
+            // Q *= scale * log2(e) (columns 0..39), columns 40..63 = 0 (column 48 will hold -m: m starts at 0)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                uint4 v = *qchunk(j);
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_half2(w[e]);
+                    w[e] = pack_half2(f.x * p.scale_log2, f.y * p.scale_log2);
+                }
+                *qchunk(j) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+#pragma unroll
+            for (int j = 5; j < 8; ++j) *qchunk(j) = make_uint4(0, 0, 0, 0);
+            if (t == 0) {   // the constant tile, one row per thread of slot 0 (BN == BM rows)
+                uint8_t* orow = sm.ones + (row >> 3) * 1024 + (row & 7) * 128;
+                *reinterpret_cast<uint4*>(orow + ((6 ^ (row & 7)) * 16)) = make_uint4(0x00003C00u, 0, 0, 0);   // 1.0, 0, ...
+                *reinterpret_cast<uint4*>(orow + ((7 ^ (row & 7)) * 16)) = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async();
+        } else if (C::ZERO_Q_PAD && ch == 0) {
+            // zero Q columns 40..47 (chunk 5)
+            *qchunk(5) = make_uint4(0, 0, 0, 0);
             fence_proxy_async();
         }
         mbar_arrive(smem_u32(&sm.q_ready));
@@ -429,6 +472,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         };
 
         for (int s = 0; s < p.n_act; ++s) {
+            // SHIFT_IN_MMA: the reference the Q K^T product subtracts (fp16-exact; -m_q sits in Q's column 48).  Every
+            // source starts from 0 - its result does not depend on the sources before it (a source listed twice at half
+            // the weight gives bit-identical output to listing it once)
+            float m_q = 0.f;
             float m = -INFINITY;  // running reference max, exp2 domain
             float l = 0.f;        // running row sum of this thread's keys (fp32, of the un-rounded probabilities)
             for (int j = 0; j < nkt; ++j) {
@@ -438,8 +485,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 uint32_t sr[CW];
                 tmem_ld_cols(s_t, sr);
                 tc_wait_ld();
-                tc_fence_before();
-                mbar_arrive(smem_u32(&sm.s_free[t]));
+                if constexpr (!C::SHIFT_IN_MMA) {
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&sm.s_free[t]));
+                }
                 // tile max (raw scores; scale > 0 so max commutes with scaling): four independent chains
                 float mxa = __uint_as_float(sr[0]), mxb = __uint_as_float(sr[1]), mxc = __uint_as_float(sr[2]),
                       mxd = __uint_as_float(sr[3]);
@@ -452,47 +501,86 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         mxd = fmax3(mxd, __uint_as_float(sr[e + 6]), __uint_as_float(sr[e + 7]));
                     }
                 }
-                const float mx = row_max(fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)), i & 1) * p.scale_log2;
                 bool waited = (i == 0);
+                float delta = 0.f;    // SHIFT_IN_MMA: what this tile's scores still have to be shifted by (0 except when
+                bool shifted = false; // the reference moved at this tile; warp-uniform flag)
+                // rare: O(i-1) must be complete before it is rescaled by alpha
+                auto rescale_o = [&](float alpha) {
+                    mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
+                    tc_fence_after();
+                    waited = true;
+                    l *= alpha;
+                    if (ch == 0) {   // one warp of the row rescales O; P V (i) waits for every warp's p_ready
+#pragma unroll
+                        for (int c = 0; c < C::NV / 16; ++c) {
+                            uint32_t ov[16];
+                            tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                            tmem_st_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
+                        }
+                        tc_wait_st();
+                    }
+                };
+                if constexpr (C::SHIFT_IN_MMA) {
+                    // the scores are already s * scale - m_q.  New reference at the first tile of a source and when the
+                    // tile maximum exceeds the current one by 2^8: an fp16-exact value, so that Q's column 48 holds it exactly
+                    const float mx = fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd));
+                    const bool move = (j == 0) || (mx > RESCALE_THRESHOLD);
+                    if (__builtin_expect(__any_sync(0xffffffffu, move) != 0, 0)) {
+                        const float m_new = move ? __half2float(__float2half_rn(m_q + mx)) : m_q;
+                        delta = m_new - m_q;   // difference of two fp16 values: exact
+                        shifted = true;        // this tile's exponentials take the copy of the code that subtracts delta
+                        if (j > 0) rescale_o(exp2f(-delta));
+                        if (move) {
+                            m_q = m_new;
+                            *reinterpret_cast<__half*>(qchunk(6)) = __float2half_rn(-m_new);
+                            fence_proxy_async();
+                        }
+                    }
+                    if (j == nkt - 1) {   // the first tile of the next source is multiplied with a zero reference again
+                        *reinterpret_cast<__half*>(qchunk(6)) = __float2half_rn(0.f);
+                        fence_proxy_async();
+                    }
+                    // S is released only now: the next Q K^T of this slot must see the new -m
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&sm.s_free[t]));
+                } else {
+                const float mx = row_max(fmaxf(fmaxf(mxa, mxb), fmaxf(mxc, mxd)), i & 1) * p.scale_log2;
                 if (j == 0) {
                     m = mx;
                 } else {
                     // every thread of a row sees the same mx and m: the RS warps of a lane quarter take the same branch
                     const bool grow = mx > m + RESCALE_THRESHOLD;
                     if (__any_sync(0xffffffffu, grow)) {
-                        // rare: O(i-1) must be complete before it is rescaled
-                        mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
-                        tc_fence_after();
-                        waited = true;
-                        const float alpha = grow ? exp2f(m - mx) : 1.f;
-                        l *= alpha;
-                        if (ch == 0) {   // one warp of the row rescales O; P V (i) waits for every warp's p_ready
-#pragma unroll
-                            for (int c = 0; c < C::NV / 16; ++c) {
-                                uint32_t ov[16];
-                                tmem_ld_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
-                                tc_wait_ld();
-#pragma unroll
-                                for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                                tmem_st_32x32b_x16(o_t + (uint32_t)(c * 16), ov);
-                            }
-                            tc_wait_st();
-                        }
+                        rescale_o(grow ? exp2f(m - mx) : 1.f);
                         if (grow) m = mx;
                     }
+                }
                 }
                 // p = 2^(s*scale - m), kept in registers as packed halves (reusing the score registers) ...
                 const float negm = -m;
                 float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
                 // HP: packed-half polynomial for part of the pairs (row sums from the ones column: nothing to add up)
-                auto exp_block = [&](auto hp_tag, auto e_begin, auto e_end) {
-                    constexpr bool HP = decltype(hp_tag)::value;
+                auto exp_block = [&](auto hp_tag, auto sh_tag, auto e_begin, auto e_end) {
+                    constexpr bool HP = decltype(hp_tag)::value, SH = decltype(sh_tag)::value;
 #pragma unroll
                     for (int e = decltype(e_begin)::value; e < decltype(e_end)::value; e += 2) {
-                        const float x0 = fmaf(__uint_as_float(sr[2 * e]), p.scale_log2, negm);
-                        const float x1 = fmaf(__uint_as_float(sr[2 * e + 1]), p.scale_log2, negm);
-                        const float x2 = fmaf(__uint_as_float(sr[2 * e + 2]), p.scale_log2, negm);
-                        const float x3 = fmaf(__uint_as_float(sr[2 * e + 3]), p.scale_log2, negm);
+                        float x0 = __uint_as_float(sr[2 * e]), x1 = __uint_as_float(sr[2 * e + 1]);
+                        float x2 = __uint_as_float(sr[2 * e + 2]), x3 = __uint_as_float(sr[2 * e + 3]);
+                        if constexpr (SH) {   // the tile at which the reference moved: scores are relative to the old one
+                            x0 -= delta;
+                            x1 -= delta;
+                            x2 -= delta;
+                            x3 -= delta;
+                        }
+                        if constexpr (!C::SHIFT_IN_MMA) {
+                            x0 = fmaf(x0, p.scale_log2, negm);
+                            x1 = fmaf(x1, p.scale_log2, negm);
+                            x2 = fmaf(x2, p.scale_log2, negm);
+                            x3 = fmaf(x3, p.scale_log2, negm);
+                        }
                         if constexpr (HP) {
                             if (hpoly_pair(e, C::HPOLY_OF_8)) sr[e] = ex2_hpoly(x0, x1);
                             else sr[e] = cvt_f16x2(ex2_f32(x0), ex2_f32(x1));
@@ -514,20 +602,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 // exponentials; the p_free spin in between also splits the basic block, so ptxas cannot sink all packs
                 // behind the last ex2 (r1o: +10 %).  The wait for P(i-1) to be consumed by its P V product overlaps the
                 // first half of the exponentials.
-                auto two_pieces = [&](auto hp_tag) {
-                    exp_block(hp_tag, integral_constant<int, 0>{}, integral_constant<int, CW / 4>{});
+                auto two_pieces = [&](auto hp_tag, auto sh_tag) {
+                    exp_block(hp_tag, sh_tag, integral_constant<int, 0>{}, integral_constant<int, CW / 4>{});
                     if (!waited) {
                         mbar_wait(smem_u32(&sm.p_free[t]), ((uint32_t)(i - 1)) & 1u);
                         tc_fence_after();
                     }
                     tmem_st_packed<0, CW / 4>(p_t, sr);
-                    exp_block(hp_tag, integral_constant<int, CW / 4>{}, integral_constant<int, CW / 2>{});
+                    exp_block(hp_tag, sh_tag, integral_constant<int, CW / 4>{}, integral_constant<int, CW / 2>{});
                     tmem_st_packed<CW / 4, CW / 4>(p_t + CW / 4, sr);
                 };
                 if (C::HPOLY_OF_8 > 0 && p.l_from_o) {
-                    two_pieces(std::true_type{});
+                    if (C::SHIFT_IN_MMA && shifted) two_pieces(std::true_type{}, std::true_type{});
+                    else two_pieces(std::true_type{}, std::false_type{});
                 } else {
-                    two_pieces(std::false_type{});
+                    if (C::SHIFT_IN_MMA && shifted) two_pieces(std::false_type{}, std::true_type{});
+                    else two_pieces(std::false_type{}, std::false_type{});
                     l += (l0 + l1) + (l2 + l3);
                 }
                 tc_wait_st();

@@ -493,14 +493,19 @@ def test_tcgen05_attention(ops, case):
     assert rel < 3e-3, (rel, mx)
 
 
-def test_tcgen05_attention_ones_column(ops):
-    """d=40 with V heads padded to 48 columns and a ones column (row sums taken from the P V product) and the
-    polynomial exp2 offload: same result as the plain layout / the oracle."""
+@pytest.mark.parametrize("N,amp", [(512, 1.0), (1024, 6.0), (384, 3.0), (128, 1.0)])
+def test_tcgen05_attention_ones_column(ops, N, amp):
+    """d=40 in the production layout: V heads padded to 48 columns with a ones column (row sums taken from the P V
+    product), part of the exponentials as packed-half polynomials, scale and running reference folded into the Q K^T
+    product.  `amp` > 1 scales q so that score ranges exceed the lazy-rescale threshold (2^8): the reference moves in the
+    middle of a source (O / l correction, -m rewritten in shared memory, the shifted copy of the exponential code).
+    N = 384 / 128: the last CTA owns one query slot only."""
     from oracle import crossview_attn as cva
-    B, N, heads, d = 4, 512, 8, 40
+    B, heads, d = 4, 8, 40
     C = heads * d
     F = B // 2
     qkv = _rand((B, N, 3 * C), 21)
+    qkv[..., :C] *= amp
     vpad = torch.zeros((B, N, heads, 48), dtype=torch.float16, device="cuda")
     vpad[..., :d] = qkv[..., 2 * C:].reshape(B, N, heads, d)
     vpad[..., d] = 1.0
