@@ -18,9 +18,11 @@
 //   the neighbouring head's columns that ride along in K contribute nothing; NV=48 (columns 40..47 of O are don't-care).
 //   With every exponential on the MUFU (exp2: 16/clk/SM) and one thread per row the kernel sat at 530 TFLOP/s: 73 % of
 //   its MUFU floor, the two softmax warps of a scheduler leaving the pipe idle whenever both were outside their
-//   exponential phase (profiles/r1i_attn_source_summary.md).  Round 3 (profiles/r3_attn.md): (a) 3 of every 8 key pairs
+//   exponential phase (profiles/r1i_attn_source_summary.md).  Since (profiles/r3_attn.md): (a) 2-3 of every 8 key pairs
 //   take a packed-half polynomial on the FMA/ALU pipes instead (ex2_hpoly; the row sums then come out of the P V
-//   product through a ones column of V) - 583 TFLOP/s; (b) two threads per row, i.e. four softmax warps per scheduler.
+//   product through a ones column of V) - 583 TFLOP/s; (b) one MMA-issuing warp per slot - 634; (c) scale and running
+//   reference folded into the Q K^T product (Cfg<40>::SHIFT_IN_MMA) - 680.  Two threads per row (four softmax warps per
+//   scheduler) is written (ROWSPLIT = 2) but loses.
 //   Measured and rejected before (profiles/r2_attn_ab.md): a third slot with BN=64 405 TFLOP/s, BN=64 with two slots
 //   405, four-piece P store 495, MUFU ping-pong 500, other MMA issue orders 442-486, ex2.approx.f16x2 (two MUFU ops
 //   in SASS) 428, fp32 polynomial 485, setmaxnreg 232/40 split 529 (r3d).
