@@ -103,7 +103,9 @@ int gcb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* 
  * ld_* are row strides in elements (>= heads*d) so q/k/v may be slices of a fused QKV projection.
  * v_head_stride: elements between consecutive heads inside a V row (both V buffers).  Normally d.  If it is >= d+8,
  * column d of every head must hold 1.0 (the caller's V projection writes it: zero weight rows + bias 1): the tcgen05
- * kernel then gets the softmax row sums out of the P V product itself instead of adding them up in registers. */
+ * kernel then gets the softmax row sums out of the P V product itself instead of adding them up in registers, and at
+ * head dim 40 evaluates a quarter of its exponentials as packed-half polynomials on the FMA pipes (no fp32
+ * probabilities to sum up any more).  Results of the two layouts agree to the fp16 rounding of the probabilities. */
 #define GCB_ATTN_AUTO 0     /* tcgen05 kernel where it is built for the shape, else the mma.sync kernel */
 #define GCB_ATTN_TCGEN05 1
 #define GCB_ATTN_MMA_SYNC 2
