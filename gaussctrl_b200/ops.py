@@ -11,7 +11,8 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (GCB_ACT_GEGLU, GCB_ACT_NONE, GCB_ACT_SILU, GCB_ATTN_AUTO, GCB_GEMM_MMA_SYNC, GCB_GEMM_TCGEN05,
+from ._lib import (GCB_ACT_GEGLU, GCB_ACT_NONE, GCB_ACT_SILU, GCB_ATTN_AUTO, GCB_ATTN_MMA_SYNC, GCB_GEMM_MMA_SYNC,
+                   GCB_GEMM_TCGEN05,
                    GCB_GEMM_TCGEN05_DIRECT, check,
                    lib)
 
@@ -204,7 +205,21 @@ def attention_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
     out = torch.empty((B, Nq, C), dtype=torch.float16, device=q.device)
     w = (ctypes.c_float * n_src)(*[float(x) for x in weights])
     sc = d ** -0.5 if scale is None else float(scale)
-    check(lib.gcb_attn_multi_fwd(_p(q), C, _p(k), _p(v), C, None, None, 0, _p(out), C, B, Nq, Nk, heads, d, d, n_src,
+    kp, vp_, ld_kv, vs = _p(k), _p(v), C, d
+    if d == 40 and Nq % 128 == 0 and Nk % 128 == 0 and _ATTN_IMPL[0] != GCB_ATTN_MMA_SYNC:
+        # the tcgen05 kernel's fast path at head dim 40 wants the V heads padded to 48 columns with a ones column (row
+        # sums out of the P V product, part of the exponentials as packed-half polynomials: 454 -> 666 TFLOP/s at
+        # B = 24, N = 4096, profiles/r3w_time_attn.txt).  K and V share one row stride in the ABI: one [k | v padded]
+        # buffer, a copy of K and V (1 % of the attention's own traffic at N = 4096)
+        Bk, ldp = k.shape[0], C + heads * 48
+        kv = torch.zeros((Bk, Nk, ldp), dtype=torch.float16, device=k.device)
+        kv[..., :C] = k
+        vv = kv[..., C:].view(Bk, Nk, heads, 48)
+        vv[..., :d] = v.view(Bk, Nk, heads, d)
+        vv[..., d] = 1.0
+        kp, vp_, ld_kv, vs = _p(kv), _p(kv, C), ldp, 48
+        LAUNCHES[0] += 4
+    check(lib.gcb_attn_multi_fwd(_p(q), C, kp, vp_, ld_kv, None, None, 0, _p(out), C, B, Nq, Nk, heads, d, vs, n_src,
                                  _p(src_index), w, sc, _ATTN_IMPL[0], _stream()))
     LAUNCHES[0] += 1
     return out
