@@ -587,9 +587,10 @@ int gcb_gemm_tc_launch(const void* x, const void* w, const void* bias, const voi
 }
 
 namespace {
-// Schedule of the next launches: -1 = by shape (product default), 0 = one tile per CTA, 1 = persistent wherever it is
-// built (TMA-store epilogue, no peers).  Set through gcb_conv2d_nhwc_fwd's impl argument (A/B tools) or GCB_GEMM_PERSIST.
-int g_schedule = -1;
+// Schedule of the calling thread's next launches: -1 = by shape (product default), 0 = one tile per CTA, 1 = persistent
+// wherever it is built (TMA-store epilogue, no peers).  Set by gcb_conv2d_nhwc_fwd from its impl argument right before
+// it launches (A/B tools), or process-wide through GCB_GEMM_PERSIST.  Per thread: concurrent callers do not interfere.
+thread_local int g_schedule = -1;
 }  // namespace
 void gcb_gemm_tc_set_schedule(int schedule) { g_schedule = schedule; }
 
