@@ -61,6 +61,23 @@ def test_parameter_spec_matches_oracle_modules():
     assert sum(int(np.prod(s)) for s in sp.unet_shapes().values()) == 859_520_964  # SD1.x UNet parameter count
 
 
+def test_ddim_tables_published_known_answers():
+    """The Stable Diffusion v1 scheduler (scheduler_config.json: scaled_linear 0.00085 -> 0.012, 1000 steps, steps_offset 1,
+    leading spacing) has published constants: sqrt(alpha_bar_T) = 0.068265 (Lin et al., "Common Diffusion Noise Schedules
+    and Sample Steps are Flawed", Table 1: Stable Diffusion's terminal SNR), alpha_bar_0 = 1 - 0.00085, and the 50-step
+    timestep list 981, 961, ..., 21, 1 of every diffusers StableDiffusionPipeline run.  Both the product tables and the
+    oracle must reproduce them."""
+    from gaussctrl_b200.sd15_spec import DDIMTables
+    from oracle import sd15
+    for tab in (DDIMTables(), sd15.DDIMTables()):
+        assert abs(float(tab.alphas_cumprod[999]) ** 0.5 - 0.068265) < 2e-6
+        assert abs(float(tab.alphas_cumprod[0]) - (1 - 0.00085)) < 1e-7
+        ts50 = [int(t) for t in tab.timesteps(50)]
+        assert ts50 == list(range(981, 0, -20))
+        assert [int(t) for t in tab.timesteps(20)] == list(range(951, 0, -50))          # the reference's 20 steps
+        assert [int(t) for t in tab.inverse_timesteps(20)] == list(range(1, 1000, 50))  # DDIMInverseScheduler: ascending
+
+
 def test_ddim_tables_match_oracle():
     from gaussctrl_b200.sd15_spec import DDIMTables
     from oracle import sd15
